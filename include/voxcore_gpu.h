@@ -1,0 +1,171 @@
+/* voxcore_gpu.h -- C ABI of libvoxcore_gpu.so, the B200 (sm_100a) implementation of Voxel Cores'
+ * data-parallel front end: inside/outside classification of the dense grid, boundary-sample
+ * ("site") extraction, the exact closest-site query per grid vertex, and the per-cell medial
+ * measures.
+ *
+ * The reference (danielyan86129/voxel_ma) has no plugin / FFI interface; its boundary is the set
+ * of C++ functions the CLI calls.  Each entry point below names the
+ * reference function (file:line under the reference tree) whose data-parallel body it replaces;
+ * INTEGRATION.md shows the call a maintainer adds at that line.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers and sizes; no exceptions, no C++/torch types.
+ *   - every call returns vc_status (0 = ok, negative = error); vc_last_error(ctx) has the text.
+ *   - host pointers are caller-owned; device memory is library-owned and freed by vc_ctx_destroy.
+ *     Pointers marked "host or device" are detected with cudaPointerGetAttributes.
+ *   - calls are synchronous for the caller unless a function says otherwise; one host thread per ctx.
+ *   - one vc_ctx per GPU (one process per GPU; multi-GPU = one ctx per rank over z-slabs).
+ *   - dense arrays are x-fastest: index = x + nx*(y + ny*z)  (MRC payload order,
+ *     3rdparty/isosurface_tao/reader.h:232-251).  A ctx owns the grid-vertex planes [z0, z1).
+ *   - there is NO CPU fallback anywhere behind this interface: without a CUDA device
+ *     vc_ctx_create fails with VC_ERR_CUDA.
+ */
+#ifndef VOXCORE_GPU_H
+#define VOXCORE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vc_ctx vc_ctx;
+
+typedef enum vc_status
+{
+    VC_OK = 0,
+    VC_ERR_INVALID = -1,     /* bad argument */
+    VC_ERR_CUDA = -2,        /* CUDA runtime error (text in vc_last_error) */
+    VC_ERR_STATE = -3,       /* call order: a prerequisite stage has not run */
+    VC_ERR_NOMEM = -4,       /* device or host allocation failed */
+    VC_ERR_UNSUPPORTED = -5  /* valid request this build does not implement */
+} vc_status;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int vc_abi_version(void);
+int vc_ctx_create(int device, vc_ctx** out);
+void vc_ctx_destroy(vc_ctx* ctx);
+const char* vc_last_error(const vc_ctx* ctx);
+/* the CUDA stream every kernel of this ctx is launched on (cudaStream_t as void*) */
+void* vc_stream(vc_ctx* ctx);
+int vc_synchronize(vc_ctx* ctx);
+/* page-locked host memory for full-speed copies (optional; any host pointer is accepted) */
+void* vc_host_alloc(size_t bytes);
+void vc_host_free(void* p);
+
+/* ---- grid and volume ------------------------------------------------------------------------
+ * Replaces the storage behind Volume3DScalar::getDataAt (include/Volume3DScalar.h:18,
+ * include/densevolume.h:36-43, 3rdparty/isosurface_tao/volume.h:217-224).
+ * vc_set_grid: global size and the z-slab [z0,z1) of grid-vertex planes this ctx owns
+ * (single GPU: z0=0, z1=nz). */
+int vc_set_grid(vc_ctx* ctx, int nx, int ny, int nz, int z0, int z1);
+/* float32 voxel planes [zlo,zhi) in MRC payload order (x fastest); `planes` points at plane zlo.
+ * Must cover [max(z0-1,0), min(z1+1,nz)) -- one halo plane each side of the slab.
+ * planes: host or device. */
+int vc_volume_upload_f32(vc_ctx* ctx, const float* planes, int zlo, int zhi);
+/* whole volume in Tao's in-memory order double[x*ny*nz + y*nz + z] (volume.h:217-224);
+ * requires the ctx to own the whole grid. */
+int vc_volume_upload_f64_zfast(vc_ctx* ctx, const double* vol);
+
+/* ---- stage 1: inside / outside ----------------------------------------------------------------
+ * a2: SpaceConverter::get_occupancy_at_vox / voxTaggedAsInside over every voxel
+ * (include/spaceinfo.h:53-58,122-129): inside <=> value > 0.0.
+ * inside_out (nullable, host or device): uint8 flags of the owned planes [z0,z1). */
+int vc_classify_grid(vc_ctx* ctx, uint8_t* inside_out);
+/* a4: VoroInfo::tagVert / tagVtsUsingUniformVol (src/voroinfo.cpp:447-494): q = M*p (double 4x4,
+ * column-major, homogeneous divide, cast to float -- XForm.h:479-489), voxel = round-half-away(q),
+ * then a2.  M == NULL means identity (what tagVert passes).  Needs vc_classify_grid first and the
+ * ctx must hold the whole grid.  xyz, out: host. */
+int vc_classify_points(vc_ctx* ctx, const float* xyz, int64_t n, const double* M, uint8_t* out);
+
+/* ---- stage 1'': boundary samples ("sites") ----------------------------------------------------
+ * a3: Surfacer::extractBoundaryVts (src/surfacing.cpp:223-321): the unique corners of all voxel
+ * faces that separate a 0-voxel from a 1-voxel, numbered in the reference's first-encounter order
+ * (x-major voxel scan, neighbour slot, corner slot).  Single-GPU form: */
+int vc_extract_sites(vc_ctx* ctx, int64_t* nsites);
+/* float32 xyz triples in site-id order (half-integer coordinates).  xyz_out: host. */
+int vc_get_sites(vc_ctx* ctx, float* xyz_out);
+/* External sample set (-siteFile / .node, src/voroUtility.cpp:74-76): replaces the extracted
+ * sites.  Sites that all lie on the half-integer corner lattice of the grid use the dense
+ * transform; any other set is served by the cell-list search. xyz: host. */
+int vc_set_sites(vc_ctx* ctx, const float* xyz, int64_t n);
+int64_t vc_num_sites(const vc_ctx* ctx);
+/* Multi-GPU form (one collective between the two calls): each rank detects the
+ * site corners of its own slab, ranks all-gather the (key, corner) records, every rank imports
+ * the union and sorts it identically.  Records: key = first-encounter key (uint64), corner =
+ * cx | cy<<21 | cz<<42 (uint64). Buffers: host or device. */
+int vc_sites_detect_local(vc_ctx* ctx, int64_t* nlocal);
+int vc_sites_export_local(vc_ctx* ctx, uint64_t* keys_out, uint64_t* corners_out);
+int vc_sites_import_global(vc_ctx* ctx, const uint64_t* keys, const uint64_t* corners, int64_t n);
+
+/* ---- stage 2: closest site ----------------------------------------------------------------------
+ * a5: the operator the reference gets from ANN, annkSearch(k=1, eps=0)
+ * (3rdparty/ann/src/kd_search.cpp:88-216; call sites src/voroinfo.cpp:344,362,
+ * src/voxelapps.cpp:204,217,331,345), with ANNbruteForce's deterministic tie rule
+ * (3rdparty/ann/src/brute.cpp:56-82): (squared distance, lowest site id).
+ * Dense form: one query per grid vertex of the owned planes.  id_out int32, d2x4_out = 4*d^2 as an
+ * exact uint32 (lattice sites; for arbitrary sites it is rounded and d2 comes from
+ * vc_closest_points).  Outputs nullable, host or device. */
+int vc_closest_grid(vc_ctx* ctx, int32_t* id_out, uint32_t* d2x4_out);
+/* Arbitrary query points: drop-in for annkSearch(q, 1, &id, &d2, 0.0); q = n x 3 doubles,
+ * d2 = squared distance in double. Host pointers. */
+int vc_closest_points(vc_ctx* ctx, const double* q, int64_t n, int32_t* id, double* d2);
+
+/* ---- stage 3: medial measures -------------------------------------------------------------------
+ * a6/a7 on the dense grid (dictionary in SURVEY section 0): per grid vertex 3 edge cells (+x,+y,+z),
+ * 3 face cells (xy,xz,yz) and the cube; lambda(2-set) = MeasureForMA::lambdaForFace
+ * (include/measureforMA_imp.h:1-4, float32), 4-/8-sets = max over their grid edges
+ * (src/voroinfo.cpp:1432-1574); cells with an outside vertex or leaving the grid report 0.
+ * Layout: edge3 / face3 = 3 planes-of-volume each (SoA: [c][z][y][x]), cube and radius one each;
+ * radius(v) = dist(site(id v), v), the m_r_per_v analogue (src/voroinfo.cpp:301-306).
+ * All outputs nullable, host or device; planes [z0,z1). Needs vc_classify_grid + vc_closest_grid. */
+int vc_cell_measures_grid(vc_ctx* ctx, float* edge3, float* face3, float* cube, float* radius);
+/* a7 on a Voronoi complex: VoroInfo::computeFacesMeasure (src/voroinfo.cpp:1552-1574). Host ptrs. */
+int vc_face_lambda(vc_ctx* ctx, const int32_t* site_pairs, int64_t nf, float* out);
+/* a8: VoroInfo::computeInfoRelatedtoSites (src/voroinfo.cpp:298-318): r[v] = dist(site, v). */
+int vc_vertex_radii(vc_ctx* ctx, const float* v_xyz, int64_t nv, const int32_t* site_of_v, float* r_out);
+/* a7 aggregation: computeEdgesMeasure / computeVertexMeasure (src/voroinfo.cpp:1432-1538):
+ * out[e] = max over items[off[e]..off[e+1]) of value[item] where valid[item] (valid nullable). */
+int vc_segment_max(vc_ctx* ctx, const int32_t* off, const int32_t* items, int64_t n, const float* value,
+                   int64_t nvalue, const uint8_t* valid, float* out);
+
+/* ---- the whole hot path in one call ----------------------------------------------------------------
+ * classify -> sites -> closest -> measures on the resident volume, all results left in device
+ * memory (fetch with vc_download).  This is one "step" of bench.py. */
+int vc_run_dense(vc_ctx* ctx, int64_t* nsites);
+typedef enum vc_array
+{
+    VC_ARR_INSIDE = 0,   /* uint8  [z][y][x]      */
+    VC_ARR_ID = 1,       /* int32  [z][y][x]      */
+    VC_ARR_D2X4 = 2,     /* uint32 [z][y][x]      */
+    VC_ARR_EDGE3 = 3,    /* float  [3][z][y][x]   */
+    VC_ARR_FACE3 = 4,    /* float  [3][z][y][x]   */
+    VC_ARR_CUBE = 5,     /* float  [z][y][x]      */
+    VC_ARR_RADIUS = 6    /* float  [z][y][x]      */
+} vc_array;
+/* copy a result array (owned planes) to dst (host or device) */
+int vc_download(vc_ctx* ctx, int which, void* dst);
+/* device pointer of a result array (valid until the next stage call / destroy) */
+void* vc_device_ptr(vc_ctx* ctx, int which);
+/* Host-buffer end-to-end step: H2D of the float32 volume, the hot path, D2H of every non-NULL
+ * output, copies and kernels overlapped plane-chunk by plane-chunk.  Pinned buffers
+ * (vc_host_alloc) reach PCIe speed. */
+int vc_run_dense_host(vc_ctx* ctx, const float* vol, uint8_t* inside, int32_t* id, uint32_t* d2x4,
+                      float* edge3, float* face3, float* cube, float* radius, int64_t* nsites);
+
+/* ---- instrumentation --------------------------------------------------------------------------------
+ * The reference's only instrumentation is struct timer around stages (include/commondefs.h:110-168);
+ * here every kernel launch can be bracketed by CUDA events on the ctx stream. */
+int vc_profile_enable(vc_ctx* ctx, int on);
+int vc_profile_reset(vc_ctx* ctx);
+/* number of distinct kernels seen; then per index: name, total ms, launches */
+int vc_profile_count(vc_ctx* ctx);
+int vc_profile_get(vc_ctx* ctx, int i, const char** name, double* total_ms, int64_t* launches);
+/* kernels launched by this ctx since creation / last reset (counted whether or not profiling is on) */
+int64_t vc_launch_count(const vc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXCORE_GPU_H */

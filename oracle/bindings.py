@@ -1,0 +1,293 @@
+"""ctypes bindings for the CPU checker -- TEST INFRASTRUCTURE ONLY.
+
+Two libraries:
+  * ``oracle/_build/liboracle.so``  the plain-C restatement (oracle/oracle.c), built by ``build_oracle()``
+  * ``oracle/_ref/libvoxref.so``    the UNMODIFIED reference compiled from /root/reference by
+                                    oracle/Makefile.ref (present only where it was built; it travels
+                                    to the GPU box as a prebuilt file)
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module.  Nothing under voxel_ma_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libvoxref.so")
+REF_CLI = os.path.join(HERE, "_ref", "main_voroUtility")
+REFERENCE_TREE = "/root/reference"
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force: bool = False) -> str:
+    """gcc-compile oracle/oracle.c (no -march, -ffp-contract=off)."""
+    src = os.path.join(HERE, "oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC",
+                               src, "-o", ORACLE_SO, "-lm"])
+    return ORACLE_SO
+
+
+def build_ref(jobs: int = 8) -> str | None:
+    """Build oracle/_ref from /root/reference when that tree is present (this container only)."""
+    if not os.path.isdir(REFERENCE_TREE):
+        return REF_SO if os.path.exists(REF_SO) else None
+    subprocess.check_call(["make", "-f", os.path.join("oracle", "Makefile.ref"), f"-j{jobs}"],
+                          cwd=ROOT, stdout=subprocess.DEVNULL)
+    return REF_SO
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        lib.orc_classify_grid_f32.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.orc_classify_grid_f64_zfast.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.orc_classify_points.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int64, C.c_void_p, _u8p]
+        lib.orc_extract_sites.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+        lib.orc_extract_sites.restype = C.c_int64
+        lib.orc_closest_points.argtypes = [_f64p, C.c_int64, C.c_int, _f64p, C.c_int64, _i32p, C.c_void_p]
+        lib.orc_closest_grid.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _i32p, C.c_void_p, C.c_void_p]
+        lib.orc_face_lambda.argtypes = [_f32p, _i32p, C.c_int64, _f32p]
+        lib.orc_vertex_radii.argtypes = [_f32p, _f32p, C.c_int64, _i32p, _f32p]
+        lib.orc_segment_max.argtypes = [_i32p, _i32p, C.c_int64, _f32p, C.c_void_p, _f32p]
+        lib.orc_cell_measures_grid.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               _f32p, _f32p, _f32p, C.c_void_p]
+        _oracle = lib
+    return _oracle
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libvoxref.so not built (make -f oracle/Makefile.ref)")
+        lib = C.CDLL(REF_SO)
+        lib.ref_set_data_dir.argtypes = [C.c_char_p]
+        lib.ref_set_data_dir(os.path.join(HERE, "_ref").encode())
+        lib.ref_classify_grid.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.ref_tag_points.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int64, _u8p]
+        lib.ref_extract_sites.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+        lib.ref_extract_sites.restype = C.c_int64
+        for f in (lib.ref_ann_kd_search, lib.ref_ann_brute_search):
+            f.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _i32p, _f64p]
+        lib.ref_ann_kd_fr_search.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _f64p, C.c_int,
+                                             _i32p, C.c_void_p, C.c_void_p]
+        lib.ref_lambda_for_face.argtypes = [_f32p, _f32p, C.c_int64, _f32p]
+        lib.ref_pipeline_run.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.ref_pipeline_run.restype = C.c_void_p
+        lib.ref_pipeline_free.argtypes = [C.c_void_p]
+        lib.ref_pipeline_count.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_pipeline_count.restype = C.c_int64
+        lib.ref_pipeline_sites.argtypes = [C.c_void_p, _f32p]
+        lib.ref_pipeline_vts.argtypes = [C.c_void_p, _f32p, _f32p, _i32p]
+        lib.ref_pipeline_faces.argtypes = [C.c_void_p, _i32p, _f32p]
+        lib.ref_pipeline_tet_vpts.argtypes = [C.c_void_p, _f32p, _u8p]
+        lib.ref_pipeline_measures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ref = lib
+    return _ref
+
+
+# ---------------------------------------------------------------- numpy-level helpers (oracle.c)
+def _dims(vol):
+    nz, ny, nx = vol.shape
+    return nx, ny, nz
+
+
+def classify_grid(vol_xfast: np.ndarray) -> np.ndarray:
+    v = np.ascontiguousarray(vol_xfast, np.float32)
+    out = np.empty(v.shape, np.uint8)
+    oracle().orc_classify_grid_f32(v, *_dims(v), out)
+    return out
+
+
+def classify_grid_f64_zfast(vol_zfast: np.ndarray, nx, ny, nz) -> np.ndarray:
+    out = np.empty((nz, ny, nx), np.uint8)
+    oracle().orc_classify_grid_f64_zfast(np.ascontiguousarray(vol_zfast, np.float64).ravel(), nx, ny, nz, out)
+    return out
+
+
+def classify_points(inside: np.ndarray, xyz: np.ndarray, M=None) -> np.ndarray:
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.empty(len(xyz), np.uint8)
+    m = None if M is None else np.ascontiguousarray(M, np.float64)
+    oracle().orc_classify_points(np.ascontiguousarray(inside, np.uint8), *_dims(inside), xyz, len(xyz),
+                                 None if m is None else m.ctypes.data, out)
+    return out
+
+
+def extract_sites(inside: np.ndarray) -> np.ndarray:
+    ins = np.ascontiguousarray(inside, np.uint8)
+    n = oracle().orc_extract_sites(ins, *_dims(ins), None, 0)
+    out = np.empty((n, 3), np.float32)
+    oracle().orc_extract_sites(ins, *_dims(ins), out.ctypes.data, n)
+    return out
+
+
+def closest_points(sites: np.ndarray, q: np.ndarray):
+    s = np.ascontiguousarray(sites, np.float64)
+    q = np.ascontiguousarray(q, np.float64)
+    dim = s.shape[1]
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float64)
+    oracle().orc_closest_points(s, len(s), dim, q, len(q), idx, d2.ctypes.data)
+    return idx, d2
+
+
+def closest_grid(sites_xyz: np.ndarray, nx, ny, nz, z0=0, z1=None, want_d2=False):
+    z1 = nz if z1 is None else z1
+    s = np.ascontiguousarray(sites_xyz, np.float32)
+    ids = np.empty((z1 - z0, ny, nx), np.int32)
+    d2x4 = np.empty((z1 - z0, ny, nx), np.uint32)
+    d2 = np.empty((z1 - z0, ny, nx), np.float64) if want_d2 else None
+    oracle().orc_closest_grid(s, len(s), nx, ny, nz, z0, z1, ids, d2x4.ctypes.data,
+                              None if d2 is None else d2.ctypes.data)
+    return (ids, d2x4, d2) if want_d2 else (ids, d2x4)
+
+
+def face_lambda(sites_xyz, site_pairs):
+    p = np.ascontiguousarray(site_pairs, np.int32).reshape(-1, 2)
+    out = np.empty(len(p), np.float32)
+    oracle().orc_face_lambda(np.ascontiguousarray(sites_xyz, np.float32), p, len(p), out)
+    return out
+
+
+def vertex_radii(sites_xyz, v_xyz, site_of_v):
+    v = np.ascontiguousarray(v_xyz, np.float32).reshape(-1, 3)
+    out = np.empty(len(v), np.float32)
+    oracle().orc_vertex_radii(np.ascontiguousarray(sites_xyz, np.float32), v, len(v),
+                              np.ascontiguousarray(site_of_v, np.int32), out)
+    return out
+
+
+def segment_max(off, items, face_lambda_, face_valid=None):
+    off = np.ascontiguousarray(off, np.int32)
+    out = np.empty(len(off) - 1, np.float32)
+    fv = None if face_valid is None else np.ascontiguousarray(face_valid, np.uint8)
+    oracle().orc_segment_max(off, np.ascontiguousarray(items, np.int32), len(out),
+                             np.ascontiguousarray(face_lambda_, np.float32),
+                             None if fv is None else fv.ctypes.data, out)
+    return out
+
+
+def cell_measures_grid(sites_xyz, ids, inside, nx, ny, nz, z0=0, z1=None, want_radius=True):
+    """ids / inside hold planes [z0, min(z1+1, nz)); outputs cover [z0, z1)."""
+    z1 = nz if z1 is None else z1
+    nzs = z1 - z0
+    e = np.empty((3, nzs, ny, nx), np.float32)
+    f = np.empty((3, nzs, ny, nx), np.float32)
+    c = np.empty((nzs, ny, nx), np.float32)
+    r = np.empty((nzs, ny, nx), np.float32) if want_radius else None
+    oracle().orc_cell_measures_grid(np.ascontiguousarray(sites_xyz, np.float32),
+                                    np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(inside, np.uint8),
+                                    nx, ny, nz, z0, z1, e, f, c, None if r is None else r.ctypes.data)
+    return e, f, c, r
+
+
+# ---------------------------------------------------------------- numpy-level helpers (real reference)
+def ref_classify_grid(vol_xfast):
+    from voxel_ma_b200.synth import to_zfast_f64
+    nx, ny, nz = _dims(vol_xfast)
+    out = np.empty((nz, ny, nx), np.uint8)
+    ref().ref_classify_grid(to_zfast_f64(vol_xfast).ravel(), nx, ny, nz, out)
+    return out
+
+
+def ref_tag_points(vol_xfast, xyz):
+    from voxel_ma_b200.synth import to_zfast_f64
+    nx, ny, nz = _dims(vol_xfast)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.empty(len(xyz), np.uint8)
+    ref().ref_tag_points(to_zfast_f64(vol_xfast).ravel(), nx, ny, nz, xyz, len(xyz), out)
+    return out
+
+
+def ref_extract_sites(vol_xfast):
+    from voxel_ma_b200.synth import to_zfast_f64
+    nx, ny, nz = _dims(vol_xfast)
+    zf = to_zfast_f64(vol_xfast).ravel()
+    n = ref().ref_extract_sites(zf, nx, ny, nz, None, 0)
+    out = np.empty((n, 3), np.float32)
+    ref().ref_extract_sites(zf, nx, ny, nz, out.ctypes.data, n)
+    return out
+
+
+def ref_ann(sites, q, brute=False):
+    s = np.ascontiguousarray(sites, np.float64)
+    q = np.ascontiguousarray(q, np.float64)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float64)
+    fn = ref().ref_ann_brute_search if brute else ref().ref_ann_kd_search
+    fn(s, len(s), s.shape[1], q, len(q), idx, d2)
+    return idx, d2
+
+
+def ref_lambda(a, b):
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    out = np.empty(len(a), np.float32)
+    ref().ref_lambda_for_face(a, b, len(a), out)
+    return out
+
+
+def ref_pipeline(vol_xfast, preprocess=False) -> dict:
+    """Run the reference's own computeVD [+ preprocessVoro + extractInsideWithMeasure] and return its
+    state as numpy arrays."""
+    from voxel_ma_b200.synth import to_zfast_f64
+    nx, ny, nz = _dims(vol_xfast)
+    L = ref()
+    h = L.ref_pipeline_run(to_zfast_f64(vol_xfast).ravel(), nx, ny, nz, 1 if preprocess else 0)
+    if not h:
+        raise RuntimeError("reference pipeline failed")
+    try:
+        cnt = lambda k: int(L.ref_pipeline_count(h, k))
+        out = {"counts": {k: cnt(i) for i, k in enumerate(
+            ["sites", "vts", "edges", "faces", "tet_vpts", "out_vts", "out_edges", "out_tris", "face_sites"])}}
+        sites = np.empty((cnt(0), 3), np.float32)
+        L.ref_pipeline_sites(h, sites)
+        out["sites"] = sites
+        tv = np.empty((cnt(4), 3), np.float32)
+        tt = np.empty(cnt(4), np.uint8)
+        L.ref_pipeline_tet_vpts(h, tv, tt)
+        out["tet_vpts"], out["tet_vtag"] = tv, tt
+        if not preprocess:
+            v = np.empty((cnt(1), 3), np.float32)
+            r = np.zeros(cnt(1), np.float32)
+            sv = np.full(cnt(1), -1, np.int32)
+            L.ref_pipeline_vts(h, v, r, sv)
+            out["vts"], out["radii"], out["site_of_v"] = v, r, sv
+            fs = np.empty((cnt(8), 2), np.int32)
+            fl = np.empty(cnt(8), np.float32)
+            L.ref_pipeline_faces(h, fs, fl)
+            out["face_sites"], out["face_lambda"] = fs, fl
+        else:
+            vm = np.empty(cnt(5), np.float32)
+            em = np.empty(cnt(6), np.float32)
+            fm = np.empty(cnt(7), np.float32)
+            L.ref_pipeline_measures(h, vm.ctypes.data, em.ctypes.data, fm.ctypes.data, None)
+            out["v_msure"], out["e_msure"], out["f_msure"] = vm, em, fm
+        return out
+    finally:
+        L.ref_pipeline_free(h)

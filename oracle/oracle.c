@@ -1,0 +1,340 @@
+/* oracle/oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU restatement of the reference's algorithm for the hot path (classify ->
+ * boundary samples -> closest sample -> medial measures).  It is the checker the CUDA path is
+ * diffed against; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load it.  The product path never calls into this file.
+ *
+ * PINNING: every function here is checked (tests/test_oracle_pinning.py, tests/golden/) against
+ *   - the reference's own code compiled unmodified into oracle/_ref/libvoxref.so
+ *     (Surfacer::extractBoundaryVts, SpaceConverter::voxTaggedAsInside, VoroInfo::tagVert,
+ *      ANNkd_tree / ANNbruteForce, MeasureForMA::lambdaForFace, VoroInfo::compute*Measure), and
+ *   - the only known-answer NN fixture in the reference tree, 3rdparty/ann/sample/sample.save.
+ * The dense per-cell measure dictionary (orc_cell_measures_grid) has no reference counterpart as
+ * an iteration space; its arithmetic (lambdaForFace + max-aggregation +
+ * validity) is pinned through the functions above, its iteration space is builder-defined.
+ * Circumradius / object angle are not implemented anywhere: "parity unpinned" for those.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC oracle/oracle.c -o oracle/_build/liboracle.so -lm
+ * (no -march: no FMA contraction, so float results have one meaning).
+ *
+ * All dense arrays are x-fastest: index = x + nx*(y + ny*z)  (the MRC payload order,
+ * 3rdparty/isosurface_tao/reader.h:232-251).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define IDX(x, y, z) ((size_t)(x) + (size_t)nx * ((size_t)(y) + (size_t)ny * (size_t)(z)))
+
+/* ---- a1/a2: getDataAt + get_occupancy_at_vox ---------------------------------------------------
+ * include/spaceinfo.h:122-129: in bounds AND getDataAt > 0.0 (double compare; -0.0, 0.0, NaN are
+ * outside); include/spaceinfo.h:108-115 bounds test; the MRC reader widens float32 samples to
+ * double (reader.h:244-246), which preserves the sign test exactly. */
+static inline int occ_f32(const float* vol, int nx, int ny, int nz, int x, int y, int z)
+{
+    if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz)
+        return 0;
+    return ((double)vol[IDX(x, y, z)] > 0.0) ? 1 : 0;
+}
+
+/* voxTaggedAsInside over the whole grid (include/spaceinfo.h:53-58). */
+void orc_classify_grid_f32(const float* vol, int nx, int ny, int nz, uint8_t* inside)
+{
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+                inside[IDX(x, y, z)] = (uint8_t)occ_f32(vol, nx, ny, nz, x, y, z);
+}
+
+/* Same on Tao's in-memory layout double[x*ny*nz + y*nz + z] (3rdparty/isosurface_tao/volume.h:217-224);
+ * output is still x-fastest. */
+void orc_classify_grid_f64_zfast(const double* vol, int nx, int ny, int nz, uint8_t* inside)
+{
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+                inside[IDX(x, y, z)] = vol[((size_t)x * ny + y) * nz + z] > 0.0 ? 1 : 0;
+}
+
+/* ---- a4: VoroInfo::tagVert (src/voroinfo.cpp:447-454) ------------------------------------------
+ * q = M * p with the double 4x4 (column-major, homogeneous divide) and a cast of each component
+ * back to float (3rdparty/trimesh2/include/XForm.h:479-489); voxel = (int)std::round(q[i]) on the
+ * FLOAT value, half away from zero (include/spaceinfo.h:93-105); then a2.  M == NULL is the
+ * identity, which is what tagVert always passes. */
+void orc_classify_points(const uint8_t* inside, int nx, int ny, int nz, const float* xyz, int64_t n,
+                         const double* M, uint8_t* out)
+{
+    static const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const double* xf = M ? M : I;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        double v0 = xyz[3 * i], v1 = xyz[3 * i + 1], v2 = xyz[3 * i + 2];
+        double h = 1 / (xf[3] * v0 + xf[7] * v1 + xf[11] * v2 + xf[15]);
+        float q0 = (float)(h * (xf[0] * v0 + xf[4] * v1 + xf[8] * v2 + xf[12]));
+        float q1 = (float)(h * (xf[1] * v0 + xf[5] * v1 + xf[9] * v2 + xf[13]));
+        float q2 = (float)(h * (xf[2] * v0 + xf[6] * v1 + xf[10] * v2 + xf[14]));
+        int x = (int)roundf(q0), y = (int)roundf(q1), z = (int)roundf(q2);
+        int in = !(x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz);
+        out[i] = (uint8_t)(in ? inside[IDX(x, y, z)] : 0);
+    }
+}
+
+/* ---- a3: Surfacer::extractBoundaryVts (src/surfacing.cpp:223-321) ------------------------------
+ * Scan voxels x outer / y / z inner (:275-284); for each of the 6 neighbours in the order
+ * -x,+x,-y,+y,-z,+z (include/surfacing.h:170-178) whose occupancy differs (out of bounds = 0,
+ * include/spaceinfo.h:125), visit the 4 corners of the shared face in the slot order of
+ * include/surfacing.h:184-190 and append a corner the first time it is seen (:254-268).
+ * Corner slots c0..c7 relative to the voxel centre: include/surfacing.h:97-119.
+ * The reference de-duplicates with unordered_map<ivec3,int> keyed by the doubled corner id
+ * (include/surfacing.h:121-136); a dense "seen" array over the (nx+1)(ny+1)(nz+1) corner lattice
+ * is the same set semantics.
+ * Returns the number of sites; writes at most cap of them (float32, half-integer coordinates). */
+static const int NB_OFF[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+static const int CORNERS_WRT_NB[6][4] = {{2, 3, 7, 6}, {0, 1, 5, 4}, {4, 6, 2, 0},
+                                         {1, 3, 7, 5}, {0, 2, 3, 1}, {5, 7, 6, 4}};
+/* corner slot -> (+1 means +0.5, 0 means -0.5) per axis */
+static const int CORNER_SIGN[8][3] = {{1, 0, 0}, {1, 1, 0}, {0, 0, 0}, {0, 1, 0},
+                                      {1, 0, 1}, {1, 1, 1}, {0, 0, 1}, {0, 1, 1}};
+
+int64_t orc_extract_sites(const uint8_t* inside, int nx, int ny, int nz, float* out_xyz, int64_t cap)
+{
+    size_t cx = (size_t)nx + 1, cy = (size_t)ny + 1, cz = (size_t)nz + 1;
+    uint8_t* seen = (uint8_t*)calloc(cx * cy * cz, 1);
+    int64_t n = 0;
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+            for (int k = 0; k < nz; ++k)
+            {
+                int cur = inside[IDX(i, j, k)];
+                for (int o = 0; o < 6; ++o)
+                {
+                    int a = i + NB_OFF[o][0], b = j + NB_OFF[o][1], c = k + NB_OFF[o][2];
+                    int nb = (a < 0 || a >= nx || b < 0 || b >= ny || c < 0 || c >= nz)
+                                 ? 0
+                                 : inside[IDX(a, b, c)];
+                    if (nb == cur)
+                        continue;
+                    for (int ii = 0; ii < 4; ++ii)
+                    {
+                        int ci = CORNERS_WRT_NB[o][ii];
+                        int px = i + CORNER_SIGN[ci][0], py = j + CORNER_SIGN[ci][1],
+                            pz = k + CORNER_SIGN[ci][2]; /* corner lattice index: coord = p - 0.5 */
+                        size_t key = (size_t)px + cx * ((size_t)py + cy * (size_t)pz);
+                        if (seen[key])
+                            continue;
+                        seen[key] = 1;
+                        if (n < cap)
+                        {
+                            out_xyz[3 * n] = (float)px - 0.5f;
+                            out_xyz[3 * n + 1] = (float)py - 0.5f;
+                            out_xyz[3 * n + 2] = (float)pz - 0.5f;
+                        }
+                        ++n;
+                    }
+                }
+            }
+    free(seen);
+    return n;
+}
+
+/* ---- a5: exact 1-NN, the contract = ANNbruteForce::annkSearch(k=1) -----------------------------
+ * 3rdparty/ann/src/brute.cpp:56-82 scans ids ascending; ANNmin_k::insert
+ * (3rdparty/ann/src/pr_queue_k.h:109-127) only displaces strictly larger keys, so among equal
+ * squared distances the LOWEST id wins.  Distance = annDist = sum over dims of (q-p)^2 in double
+ * (3rdparty/ann/src/ANN.cpp:43-58; ANNcoord/ANNdist are double, include/ANN/ANN.h:160-161),
+ * accumulated in dimension order.  The kd-tree (kd_search.cpp:88-216) returns the same d2 but
+ * its tie choice depends on traversal order; d2 is compared against it, ids
+ * against this function. */
+void orc_closest_points(const double* sites, int64_t ns, int dim, const double* q, int64_t nq,
+                        int32_t* idx, double* d2)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nq; ++i)
+    {
+        double best = INFINITY;
+        int32_t bi = -1;
+        const double* qq = q + (size_t)i * dim;
+        for (int64_t s = 0; s < ns; ++s)
+        {
+            const double* p = sites + (size_t)s * dim;
+            double d = 0;
+            for (int k = 0; k < dim; ++k)
+            {
+                double t = qq[k] - p[k];
+                d = d + t * t;
+            }
+            if (d < best)
+            {
+                best = d;
+                bi = (int32_t)s;
+            }
+        }
+        idx[i] = bi;
+        if (d2)
+            d2[i] = best;
+    }
+}
+
+/* Dense query set: one query per grid vertex (integer lattice point) against float32 sites widened
+ * to double exactly as the reference widens them for ANN (src/voroinfo.cpp:336-341).  Outputs the
+ * id and 4*d2 as an exact integer (sites on the half-integer lattice make 4*d2 integral; for
+ * arbitrary sites d2x4 may be NULL and d2 is returned in double). */
+void orc_closest_grid(const float* sites_xyz, int64_t ns, int nx, int ny, int nz, int z0, int z1,
+                      int32_t* id_out, uint32_t* d2x4_out, double* d2_out)
+{
+    double* S = (double*)malloc((size_t)ns * 3 * sizeof(double));
+    for (int64_t i = 0; i < ns * 3; ++i)
+        S[i] = (double)sites_xyz[i];
+#pragma omp parallel for schedule(dynamic, 64) collapse(2)
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+            {
+                double best = INFINITY;
+                int32_t bi = -1;
+                for (int64_t s = 0; s < ns; ++s)
+                {
+                    double t0 = (double)x - S[3 * s], t1 = (double)y - S[3 * s + 1],
+                           t2 = (double)z - S[3 * s + 2];
+                    double d = 0;
+                    d = d + t0 * t0;
+                    d = d + t1 * t1;
+                    d = d + t2 * t2;
+                    if (d < best)
+                    {
+                        best = d;
+                        bi = (int32_t)s;
+                    }
+                }
+                size_t o = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)(z - z0));
+                id_out[o] = bi;
+                if (d2x4_out)
+                    d2x4_out[o] = (uint32_t)llround(4.0 * best);
+                if (d2_out)
+                    d2_out[o] = best;
+            }
+    free(S);
+}
+
+/* ---- a6: MeasureForMA::lambdaForFace = trimesh::dist (include/measureforMA_imp.h:1-4,
+ * 3rdparty/trimesh2/include/Vec.h:1128-1143): float32, d2 = sqr(b0-a0); d2 += sqr(b_i-a_i);
+ * sqrt in float. */
+static inline float lambda_f(const float* a, const float* b)
+{
+    float t = b[0] - a[0];
+    float d2 = t * t;
+    t = b[1] - a[1];
+    d2 += t * t;
+    t = b[2] - a[2];
+    d2 += t * t;
+    return sqrtf(d2);
+}
+
+/* a7, face form: VoroInfo::computeFacesMeasure (src/voroinfo.cpp:1552-1574):
+ * lambda(f) = lambdaForFace(site[pair[0]], site[pair[1]]). */
+void orc_face_lambda(const float* sites_xyz, const int32_t* site_pairs, int64_t nf, float* out)
+{
+    for (int64_t f = 0; f < nf; ++f)
+        out[f] = lambda_f(sites_xyz + 3 * (size_t)site_pairs[2 * f],
+                          sites_xyz + 3 * (size_t)site_pairs[2 * f + 1]);
+}
+
+/* a8: VoroInfo::computeInfoRelatedtoSites (src/voroinfo.cpp:298-318): r[v] = dist(site, v) with
+ * the argument order (site_p, v_p); the caller supplies the site each vertex ends up with. */
+void orc_vertex_radii(const float* sites_xyz, const float* v_xyz, int64_t nv, const int32_t* site_of_v,
+                      float* r_out)
+{
+    for (int64_t v = 0; v < nv; ++v)
+        r_out[v] = site_of_v[v] < 0 ? 0.0f
+                                    : lambda_f(sites_xyz + 3 * (size_t)site_of_v[v], v_xyz + 3 * v);
+}
+
+/* a7, aggregation form: computeEdgesMeasure / computeVertexMeasure (src/voroinfo.cpp:1490-1538,
+ * 1432-1488): max of the face lambdas over the incident VALID faces, 0 when there are none.
+ * CSR adjacency: element e owns items[off[e] .. off[e+1]). */
+void orc_segment_max(const int32_t* off, const int32_t* items, int64_t n, const float* face_lambda,
+                     const uint8_t* face_valid, float* out)
+{
+    for (int64_t e = 0; e < n; ++e)
+    {
+        float m = 0.0f;
+        for (int32_t k = off[e]; k < off[e + 1]; ++k)
+        {
+            int32_t f = items[k];
+            if (face_valid && !face_valid[f])
+                continue;
+            m = face_lambda[f] > m ? face_lambda[f] : m; /* std::max(m, f_lmd) */
+        }
+        out[e] = m;
+    }
+}
+
+/* ---- dense cell measures: the grid-cell <-> Voronoi-cell dictionary of SURVEY section 0 ---------
+ * 7 cells anchored at each grid vertex v=(x,y,z): edges +x,+y,+z; faces xy,xz,yz; the cube.
+ *   lambda_edge(u,w) = lambdaForFace(s(id u), s(id w))                      (src/voroinfo.cpp:1564-1568)
+ *   lambda_face      = max over the face's 4 grid edges                     (:1505-1523)
+ *   lambda_cube      = max over the cube's 12 grid edges                    (:1447-1470)
+ * A cell is valid iff all its vertices are inside (computeFaceValidity, include/voroinfo_imp.h:26-34);
+ * invalid cells and cells that would leave the grid report 0 (:1460-1461, 1513-1514).
+ * radius(v) = dist(s(id v), v) in float (the m_r_per_v analogue, :301-306).
+ * Planes are SoA: edge3[c][v], face3[c][v] with c = 0,1,2 (edges +x,+y,+z; faces xy,xz,yz).
+ * id / inside cover planes [z0, z1 + 1) when z1 < nz (one halo plane), outputs cover [z0, z1). */
+void orc_cell_measures_grid(const float* sites_xyz, const int32_t* id, const uint8_t* inside, int nx,
+                            int ny, int nz, int z0, int z1, float* edge3, float* face3, float* cube,
+                            float* radius)
+{
+    int zh = z1 < nz ? z1 + 1 : z1; /* planes available */
+    size_t plane = (size_t)nx * ny, nv = plane * (size_t)(z1 - z0);
+#define L(x, y, z) ((size_t)(x) + (size_t)nx * ((size_t)(y) + (size_t)ny * (size_t)((z) - z0)))
+#pragma omp parallel for schedule(static)
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+            {
+                size_t o = L(x, y, z);
+                /* the 8 cube vertices, bit0 = +x, bit1 = +y, bit2 = +z */
+                const float* s[8];
+                int in[8], ok[8];
+                for (int c = 0; c < 8; ++c)
+                {
+                    int xx = x + (c & 1), yy = y + ((c >> 1) & 1), zz = z + ((c >> 2) & 1);
+                    ok[c] = xx < nx && yy < ny && zz < zh && zz < nz;
+                    in[c] = ok[c] ? inside[L(xx, yy, zz)] : 0;
+                    s[c] = ok[c] ? sites_xyz + 3 * (size_t)id[L(xx, yy, zz)] : NULL;
+                }
+                /* 12 cube edges as vertex pairs; the first endpoint is the lower vertex */
+                static const int E[12][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7},  /* x edges */
+                                             {0, 2}, {1, 3}, {4, 6}, {5, 7},  /* y edges */
+                                             {0, 4}, {1, 5}, {2, 6}, {3, 7}}; /* z edges */
+                float le[12];
+                for (int e = 0; e < 12; ++e)
+                    le[e] = (ok[E[e][0]] && ok[E[e][1]]) ? lambda_f(s[E[e][0]], s[E[e][1]]) : 0.0f;
+#define MAX2(a, b) ((a) > (b) ? (a) : (b))
+                edge3[0 * nv + o] = (in[0] && in[1]) ? le[0] : 0.0f;
+                edge3[1 * nv + o] = (in[0] && in[2]) ? le[4] : 0.0f;
+                edge3[2 * nv + o] = (in[0] && in[4]) ? le[8] : 0.0f;
+                /* faces: xy = {0,1,2,3}, xz = {0,1,4,5}, yz = {0,2,4,6} */
+                float fxy = MAX2(MAX2(le[0], le[1]), MAX2(le[4], le[5]));
+                float fxz = MAX2(MAX2(le[0], le[2]), MAX2(le[8], le[9]));
+                float fyz = MAX2(MAX2(le[4], le[6]), MAX2(le[8], le[10]));
+                face3[0 * nv + o] = (in[0] && in[1] && in[2] && in[3]) ? fxy : 0.0f;
+                face3[1 * nv + o] = (in[0] && in[1] && in[4] && in[5]) ? fxz : 0.0f;
+                face3[2 * nv + o] = (in[0] && in[2] && in[4] && in[6]) ? fyz : 0.0f;
+                float m = 0.0f;
+                for (int e = 0; e < 12; ++e)
+                    m = MAX2(m, le[e]);
+                int all = 1;
+                for (int c = 0; c < 8; ++c)
+                    all = all && in[c];
+                cube[o] = all ? m : 0.0f;
+                if (radius)
+                {
+                    float v[3] = {(float)x, (float)y, (float)z};
+                    radius[o] = lambda_f(s[0], v);
+                }
+            }
+#undef L
+#undef MAX2
+}

@@ -1,0 +1,108 @@
+// tests/host_harness.cpp -- TEST ONLY.  Drives the exact-arithmetic core the CUDA kernels are built
+// from (voxel_ma_b200/csrc/vc_core.h: vc_site_key, vc_nearest_on_zline, vc_envelope_line, vc_sep)
+// line by line on the CPU, so the algorithm can be checked against the oracle in the `not gpu`
+// suite.  Nothing here is reachable from the product library.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../voxel_ma_b200/csrc/vc_core.h"
+
+extern "C"
+{
+    // site numbering: corners of the whole grid -> sites in reference order. Returns count.
+    int64_t hh_sites(const uint8_t* inside, int nx, int ny, int nz, float* out_xyz, int64_t cap)
+    {
+        std::vector<std::pair<vc_u64, vc_u64>> recs;
+        auto occ_at = [&](int x, int y, int z, uint32_t& inb) -> uint32_t
+        {
+            if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz)
+            {
+                inb = 0;
+                return 0;
+            }
+            inb = 1;
+            return inside[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z)] ? 1u : 0u;
+        };
+        for (int cz = 0; cz <= nz; ++cz)
+            for (int cy = 0; cy <= ny; ++cy)
+                for (int cx = 0; cx <= nx; ++cx)
+                {
+                    uint32_t occ = 0, inb = 0;
+                    for (int bit = 0; bit < 8; ++bit)
+                    {
+                        uint32_t ib;
+                        uint32_t o = occ_at(cx - 1 + (bit >> 2), cy - 1 + ((bit >> 1) & 1), cz - 1 + (bit & 1), ib);
+                        occ |= o << bit;
+                        inb |= ib << bit;
+                    }
+                    vc_u64 k = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
+                    if (k != VC_INF)
+                        recs.emplace_back(k, vc_pack_corner(cx, cy, cz));
+                }
+        std::sort(recs.begin(), recs.end());
+        int64_t n = (int64_t)recs.size();
+        for (int64_t i = 0; i < n && i < cap; ++i)
+        {
+            int cx, cy, cz;
+            vc_unpack_corner(recs[i].second, cx, cy, cz);
+            out_xyz[3 * i] = (float)cx - 0.5f;
+            out_xyz[3 * i + 1] = (float)cy - 0.5f;
+            out_xyz[3 * i + 2] = (float)cz - 0.5f;
+        }
+        return n;
+    }
+
+    // separable exact transform with the kernels' data layout:
+    //   pass Z: z-line site lists -> G1[vz][cx][cy];  pass X: -> G2[vz][cy][vx];  pass Y: -> out[vz][vy][vx]
+    // sites: corner indices (cx,cy,cz) per site id. Output planes [z0,z1).
+    void hh_closest_grid(const int32_t* corners, int64_t ns, int nx, int ny, int nz, int z0, int z1,
+                         int32_t* id_out, uint32_t* d2x4_out)
+    {
+        const int CX = nx + 1, CY = ny + 1;
+        const int nzs = z1 - z0;
+        // line lists
+        std::vector<std::vector<vc_u64>> lines((size_t)CX * CY);
+        for (int64_t s = 0; s < ns; ++s)
+            lines[(size_t)corners[3 * s] * CY + corners[3 * s + 1]].push_back(
+                ((vc_u64)corners[3 * s + 2] << 32) | (uint32_t)s);
+        for (auto& l : lines)
+            std::sort(l.begin(), l.end());
+        std::vector<vc_u64> G1((size_t)nzs * CX * CY), G2((size_t)nzs * CY * nx);
+        for (int cx = 0; cx < CX; ++cx)
+            for (int cy = 0; cy < CY; ++cy)
+            {
+                const auto& l = lines[(size_t)cx * CY + cy];
+                int last = (int)l.size();
+                int lo = -1;
+                for (int vz = z0; vz < z1; ++vz)
+                {
+                    while (lo + 1 < last && (int)(l[lo + 1] >> 32) <= vz)
+                        ++lo;
+                    G1[((size_t)(vz - z0) * CX + cx) * CY + cy] = vc_nearest_on_zline(l.data(), 0, last, lo, vz);
+                }
+            }
+        int maxc = std::max(CX, CY) + 1;
+        std::vector<vc_u64> stH(maxc);
+        std::vector<uint32_t> stPT(maxc);
+        for (int vz = 0; vz < nzs; ++vz)
+            for (int cy = 0; cy < CY; ++cy)
+            {
+                vc_u64* row = &G2[((size_t)vz * CY + cy) * nx];
+                vc_envelope_line(&G1[(size_t)vz * CX * CY + cy], (long)CY, CX, nx, stH.data(), stPT.data(),
+                                 [&](int t, vc_u64 v) { row[t] = v; });
+            }
+        for (int vz = 0; vz < nzs; ++vz)
+            for (int vx = 0; vx < nx; ++vx)
+                vc_envelope_line(&G2[(size_t)vz * CY * nx + vx], (long)nx, CY, ny, stH.data(), stPT.data(),
+                                 [&](int t, vc_u64 v)
+                                 {
+                                     size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
+                                     id_out[o] = (int32_t)(uint32_t)v;
+                                     d2x4_out[o] = (uint32_t)(v >> 32);
+                                 });
+    }
+
+    int hh_floor_div(int a, int b) { return vc_floor_div(a, b); }
+}

@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/voxcore_gpu.h), against the
+CPU oracle (oracle/oracle.c, pinned to the reference in test_oracle_pinning.py) on the same seeded
+inputs.  Integer / index / flag results must be bit-exact; float32 measures must be bit-exact too
+(BASELINE: "within 1e-9 relative" -- the tolerance used below is 0)."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from tests.cases import small_cases
+from voxel_ma_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = small_cases()
+
+
+@pytest.fixture(scope="module")
+def ctx(ctx_factory):
+    return ctx_factory()
+
+
+def _run_all(ctx, vol):
+    nz, ny, nx = vol.shape
+    ctx.set_grid(nx, ny, nz)
+    ctx.upload_volume(vol)
+    inside = ctx.classify_grid()
+    n = ctx.extract_sites()
+    sites = ctx.get_sites()
+    assert len(sites) == n
+    return inside, sites
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_classify_and_sites_bit_exact(ctx, name):
+    vol = CASES[name]
+    inside, sites = _run_all(ctx, vol)
+    o_inside = ob.classify_grid(vol)
+    assert np.array_equal(inside, o_inside)
+    o_sites = ob.extract_sites(o_inside)
+    assert sites.shape == o_sites.shape
+    assert np.array_equal(sites, o_sites), "site order must be the reference's first-encounter order"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_closest_grid_bit_exact(ctx, name):
+    vol = CASES[name]
+    inside, sites = _run_all(ctx, vol)
+    if len(sites) == 0:
+        pytest.skip("no boundary")
+    nz, ny, nx = vol.shape
+    ids, d2x4 = ctx.closest_grid()
+    o_ids, o_d2x4 = ob.closest_grid(sites, nx, ny, nz)
+    assert np.array_equal(d2x4, o_d2x4)
+    assert np.array_equal(ids, o_ids), "ties must go to the lowest site id (ANNbruteForce rule)"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cell_measures_bit_exact(ctx, name):
+    vol = CASES[name]
+    inside, sites = _run_all(ctx, vol)
+    if len(sites) == 0:
+        pytest.skip("no boundary")
+    nz, ny, nx = vol.shape
+    ids, _ = ctx.closest_grid()
+    e, f, c, r = ctx.cell_measures_grid()
+    oe, of, oc, orad = ob.cell_measures_grid(sites, ids, inside, nx, ny, nz)
+    for got, want, what in ((e, oe, "edge"), (f, of, "face"), (c, oc, "cube"), (r, orad, "radius")):
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), what  # tolerance: 0 ulp
+
+
+def test_run_dense_matches_staged(ctx):
+    vol = synth.sphere(48)
+    inside, sites = _run_all(ctx, vol)
+    ids, d2 = ctx.closest_grid()
+    e, f, c, r = ctx.cell_measures_grid()
+    n = ctx.run_dense()
+    assert n == len(sites)
+    assert np.array_equal(ctx.download(api.ARR_INSIDE), inside)
+    assert np.array_equal(ctx.download(api.ARR_ID), ids)
+    assert np.array_equal(ctx.download(api.ARR_D2X4), d2)
+    assert np.array_equal(ctx.download(api.ARR_EDGE3), e)
+    assert np.array_equal(ctx.download(api.ARR_FACE3), f)
+    assert np.array_equal(ctx.download(api.ARR_CUBE), c)
+    assert np.array_equal(ctx.download(api.ARR_RADIUS), r)
+
+
+def test_run_dense_host_matches(ctx):
+    vol = synth.torus(56)
+    nz, ny, nx = vol.shape
+    ctx.set_grid(nx, ny, nz)
+    s = (nz, ny, nx)
+    inside = np.empty(s, np.uint8)
+    ids = np.empty(s, np.int32)
+    d2 = np.empty(s, np.uint32)
+    e, f = np.empty((3,) + s, np.float32), np.empty((3,) + s, np.float32)
+    c, r = np.empty(s, np.float32), np.empty(s, np.float32)
+    n = ctx.run_dense_host(vol, inside, ids, d2, e, f, c, r)
+    o_inside = ob.classify_grid(vol)
+    o_sites = ob.extract_sites(o_inside)
+    assert n == len(o_sites)
+    o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
+    assert np.array_equal(inside, o_inside) and np.array_equal(ids, o_ids) and np.array_equal(d2, o_d2)
+    oe, of, oc, orad = ob.cell_measures_grid(o_sites, o_ids, o_inside, nx, ny, nz)
+    assert np.array_equal(e, oe) and np.array_equal(f, of) and np.array_equal(c, oc) and np.array_equal(r, orad)
+
+
+def test_f64_zfast_upload(ctx):
+    vol = synth.sphere(24)
+    nz, ny, nx = vol.shape
+    ctx.upload_volume_f64_zfast(synth.to_zfast_f64(vol), nx, ny, nz)
+    inside = ctx.classify_grid()
+    assert np.array_equal(inside, ob.classify_grid(vol))
+    assert ctx.extract_sites() == len(ob.extract_sites(inside))
+
+
+def test_slab_contexts_reproduce_whole_grid(ctx_factory):
+    """z-slab sharding on one device: two contexts, halo recompute, site exchange through host
+    buffers -- the same calls the multi-GPU path makes around its all-gather."""
+    vol = synth.assembly(40, count=10)
+    nz, ny, nx = vol.shape
+    whole = ctx_factory()
+    inside, sites = _run_all(whole, vol)
+    ids, d2 = whole.closest_grid()
+    e, f, c, r = whole.cell_measures_grid()
+    cuts = [0, 13, 40]
+    parts = [ctx_factory() for _ in range(2)]
+    recs = []
+    for k, p in enumerate(parts):
+        z0, z1 = cuts[k], cuts[k + 1]
+        p.set_grid(nx, ny, nz, z0, z1)
+        lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
+        p.upload_volume(vol[lo:hi], zlo=lo)
+        assert np.array_equal(p.classify_grid(), inside[z0:z1])
+        n = p.sites_detect_local()
+        keys, corners = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        p.sites_export_local(keys, corners)
+        recs.append((keys, corners))
+    keys = np.concatenate([k for k, _ in recs])
+    corners = np.concatenate([c for _, c in recs])
+    assert len(keys) == len(sites)
+    for k, p in enumerate(parts):
+        z0, z1 = cuts[k], cuts[k + 1]
+        p.sites_import_global(keys, corners, len(keys))
+        assert np.array_equal(p.get_sites(), sites)
+        pi, pd = p.closest_grid()
+        assert np.array_equal(pi, ids[z0:z1]) and np.array_equal(pd, d2[z0:z1])
+        pe, pf, pc, pr = p.cell_measures_grid()
+        assert np.array_equal(pe, e[:, z0:z1]) and np.array_equal(pf, f[:, z0:z1])
+        assert np.array_equal(pc, c[z0:z1]) and np.array_equal(pr, r[z0:z1])
+
+
+def test_set_sites_lattice_and_points(ctx):
+    vol = synth.sphere(32)
+    inside, sites = _run_all(ctx, vol)
+    nz, ny, nx = vol.shape
+    # external sample set in a different order: ids follow the given order
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(sites))
+    ext = sites[perm]
+    ctx.set_sites(ext)
+    ids, d2 = ctx.closest_grid()
+    o_ids, o_d2 = ob.closest_grid(ext, nx, ny, nz)
+    assert np.array_equal(ids, o_ids) and np.array_equal(d2, o_d2)
+    # arbitrary query points: drop-in for annkSearch(k=1, eps=0)
+    q = rng.uniform(-3, 35, size=(4000, 3))
+    q[:500] = np.round(q[:500] * 2) / 2  # many exact ties on the half-integer lattice
+    pid, pd2 = ctx.closest_points(q)
+    oid, od2 = ob.closest_points(ext, q)
+    assert np.array_equal(pd2, od2)
+    assert np.array_equal(pid, oid)
+
+
+def test_general_sites_cell_list(ctx):
+    rng = np.random.default_rng(11)
+    nx, ny, nz = 24, 20, 16
+    ctx.set_grid(nx, ny, nz)
+    sites = rng.uniform(0, 20, size=(700, 3)).astype(np.float32)
+    sites[100:110] = sites[90:100]  # duplicates: lowest id must win
+    ctx.set_sites(sites)
+    q = rng.uniform(-5, 30, size=(3000, 3))
+    pid, pd2 = ctx.closest_points(q)
+    oid, od2 = ob.closest_points(sites, q)
+    assert np.array_equal(pd2, od2) and np.array_equal(pid, oid)
+    ids, _ = ctx.closest_grid()
+    o_ids, _, o_d2 = ob.closest_grid(sites, nx, ny, nz, want_d2=True)
+    assert np.array_equal(ids, o_ids)
+
+
+def test_complex_side_operators(ctx):
+    vol = synth.sphere(32)
+    inside, sites = _run_all(ctx, vol)
+    rng = np.random.default_rng(5)
+    pairs = rng.integers(0, len(sites), size=(5000, 2)).astype(np.int32)
+    assert np.array_equal(ctx.face_lambda(pairs), ob.face_lambda(sites, pairs))
+    v = rng.uniform(0, 31, size=(5000, 3)).astype(np.float32)
+    sv = rng.integers(-1, len(sites), size=5000).astype(np.int32)
+    assert np.array_equal(ctx.vertex_radii(v, sv), ob.vertex_radii(sites, v, sv))
+    # tagVert on points that sit exactly on voxel boundaries (round half away from zero)
+    p = rng.uniform(-2, 34, size=(6000, 3)).astype(np.float32)
+    p[:3000] = np.round(p[:3000] * 2) / 2
+    assert np.array_equal(ctx.classify_points(p), ob.classify_points(inside, p))
+    M = np.array([0.5, 0, 0, 0, 0, 0.25, 0, 0, 0, 0, 2.0, 0, 1.0, -2.0, 3.0, 1.0])
+    assert np.array_equal(ctx.classify_points(p, M), ob.classify_points(inside, p, M))
+    # max aggregation over CSR adjacency
+    lam = ctx.face_lambda(pairs)
+    counts = rng.integers(0, 6, size=900)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    items = rng.integers(0, len(lam), size=off[-1]).astype(np.int32)
+    valid = (rng.random(len(lam)) > 0.3).astype(np.uint8)
+    assert np.array_equal(ctx.segment_max(off, items, lam, valid), ob.segment_max(off, items, lam, valid))
+
+
+def test_errors_are_reported(ctx_factory):
+    c = ctx_factory()
+    with pytest.raises(api.VoxcoreError):
+        c.classify_grid()  # no grid / volume yet
+    c.set_grid(8, 8, 8)
+    with pytest.raises(api.VoxcoreError):
+        c.closest_grid()  # no sites
+    with pytest.raises(api.VoxcoreError):
+        c.set_grid(4096, 8, 8)

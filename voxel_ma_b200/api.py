@@ -1,0 +1,321 @@
+"""Python binding of the C ABI (include/voxcore_gpu.h) -- used by tests/ and bench.py.
+
+Every call goes through ``libvoxcore_gpu.so`` (hand-written CUDA, sm_100a).  There is no CPU
+fallback: if the library is missing or no CUDA device is visible, constructing a ``Context``
+raises.  Arrays are numpy, x fastest: ``vol[z, y, x]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libvoxcore_gpu.so")
+
+VC_OK = 0
+ARR_INSIDE, ARR_ID, ARR_D2X4, ARR_EDGE3, ARR_FACE3, ARR_CUBE, ARR_RADIUS = range(7)
+
+# every symbol include/voxcore_gpu.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "vc_abi_version", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
+    "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_f64_zfast",
+    "vc_classify_grid", "vc_classify_points", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
+    "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_closest_grid",
+    "vc_closest_points", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max",
+    "vc_run_dense", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
+    "vc_profile_count", "vc_profile_get", "vc_launch_count",
+]
+
+
+class VoxcoreError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen libvoxcore_gpu.so; raises if it has not been built (python -m voxel_ma_b200.build)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise VoxcoreError(f"{p} is missing: build it with `python -m voxel_ma_b200.build` "
+                           "(there is no CPU fallback for this path)")
+    lib = C.CDLL(p)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.vc_abi_version.restype = i32
+    lib.vc_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.vc_ctx_destroy.argtypes = [vp]
+    lib.vc_ctx_destroy.restype = None
+    lib.vc_last_error.argtypes = [vp]
+    lib.vc_last_error.restype = C.c_char_p
+    lib.vc_stream.argtypes = [vp]
+    lib.vc_stream.restype = vp
+    lib.vc_synchronize.argtypes = [vp]
+    lib.vc_host_alloc.argtypes = [C.c_size_t]
+    lib.vc_host_alloc.restype = vp
+    lib.vc_host_free.argtypes = [vp]
+    lib.vc_host_free.restype = None
+    lib.vc_set_grid.argtypes = [vp, i32, i32, i32, i32, i32]
+    lib.vc_volume_upload_f32.argtypes = [vp, vp, i32, i32]
+    lib.vc_volume_upload_f64_zfast.argtypes = [vp, vp]
+    lib.vc_classify_grid.argtypes = [vp, vp]
+    lib.vc_classify_points.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_extract_sites.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_get_sites.argtypes = [vp, vp]
+    lib.vc_set_sites.argtypes = [vp, vp, i64]
+    lib.vc_num_sites.argtypes = [vp]
+    lib.vc_num_sites.restype = i64
+    lib.vc_sites_detect_local.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_sites_export_local.argtypes = [vp, vp, vp]
+    lib.vc_sites_import_global.argtypes = [vp, vp, vp, i64]
+    lib.vc_closest_grid.argtypes = [vp, vp, vp]
+    lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_cell_measures_grid.argtypes = [vp, vp, vp, vp, vp]
+    lib.vc_face_lambda.argtypes = [vp, vp, i64, vp]
+    lib.vc_vertex_radii.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_segment_max.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp]
+    lib.vc_run_dense.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_download.argtypes = [vp, i32, vp]
+    lib.vc_device_ptr.argtypes = [vp, i32]
+    lib.vc_device_ptr.restype = vp
+    lib.vc_run_dense_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.vc_profile_enable.argtypes = [vp, i32]
+    lib.vc_profile_reset.argtypes = [vp]
+    lib.vc_profile_count.argtypes = [vp]
+    lib.vc_profile_get.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.vc_launch_count.argtypes = [vp]
+    lib.vc_launch_count.restype = i64
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from vc_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = self._lib.vc_host_alloc(max(n, 1))
+        if not self._p:
+            raise VoxcoreError("vc_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None):
+                self.array = None
+                self._lib.vc_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context = one z-slab of the grid (the whole grid on a single GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.vc_ctx_create(device, C.byref(h))
+        if st != VC_OK:
+            raise VoxcoreError(f"vc_ctx_create(device={device}) failed with {st}: no usable CUDA device "
+                               "(this path has no CPU fallback)")
+        self.h = h
+        self.nx = self.ny = self.nz = self.z0 = self.z1 = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st != VC_OK:
+            raise VoxcoreError(f"status {st}: {self.lib.vc_last_error(self.h).decode()}")
+
+    # ---- grid / volume
+    def set_grid(self, nx, ny, nz, z0=0, z1=None):
+        z1 = nz if z1 is None else z1
+        self._ck(self.lib.vc_set_grid(self.h, nx, ny, nz, z0, z1))
+        self.nx, self.ny, self.nz, self.z0, self.z1 = nx, ny, nz, z0, z1
+
+    @property
+    def slab_shape(self):
+        return (self.z1 - self.z0, self.ny, self.nx)
+
+    def upload_volume(self, vol: np.ndarray, zlo: int = 0):
+        """vol[z,y,x] float32 planes starting at global plane zlo (whole volume: zlo=0)."""
+        v = np.ascontiguousarray(vol, np.float32)
+        if not self.nx:
+            nz, ny, nx = v.shape
+            self.set_grid(nx, ny, nz)
+        self._ck(self.lib.vc_volume_upload_f32(self.h, _ptr(v), zlo, zlo + v.shape[0]))
+
+    def upload_volume_f64_zfast(self, vol_zfast: np.ndarray, nx, ny, nz):
+        self.set_grid(nx, ny, nz)
+        v = np.ascontiguousarray(vol_zfast, np.float64)
+        self._ck(self.lib.vc_volume_upload_f64_zfast(self.h, _ptr(v)))
+
+    # ---- stages
+    def classify_grid(self, fetch=True):
+        out = np.empty(self.slab_shape, np.uint8) if fetch else None
+        self._ck(self.lib.vc_classify_grid(self.h, _ptr(out)))
+        return out
+
+    def classify_points(self, xyz, M=None):
+        p = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        out = np.empty(len(p), np.uint8)
+        m = None if M is None else np.ascontiguousarray(M, np.float64)
+        self._ck(self.lib.vc_classify_points(self.h, _ptr(p), len(p), _ptr(m), _ptr(out)))
+        return out
+
+    def extract_sites(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_extract_sites(self.h, C.byref(n)))
+        return n.value
+
+    def num_sites(self) -> int:
+        return int(self.lib.vc_num_sites(self.h))
+
+    def get_sites(self) -> np.ndarray:
+        out = np.empty((max(self.num_sites(), 0), 3), np.float32)
+        self._ck(self.lib.vc_get_sites(self.h, _ptr(out)))
+        return out
+
+    def set_sites(self, xyz):
+        p = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self._ck(self.lib.vc_set_sites(self.h, _ptr(p), len(p)))
+
+    def sites_detect_local(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_sites_detect_local(self.h, C.byref(n)))
+        return n.value
+
+    def sites_export_local(self, keys, corners):
+        """keys / corners: numpy uint64 arrays or raw device pointers (int)."""
+        self._ck(self.lib.vc_sites_export_local(self.h, _ptr(keys), _ptr(corners)))
+
+    def sites_import_global(self, keys, corners, n):
+        self._ck(self.lib.vc_sites_import_global(self.h, _ptr(keys), _ptr(corners), n))
+
+    def closest_grid(self, fetch=True):
+        ids = np.empty(self.slab_shape, np.int32) if fetch else None
+        d2 = np.empty(self.slab_shape, np.uint32) if fetch else None
+        self._ck(self.lib.vc_closest_grid(self.h, _ptr(ids), _ptr(d2)))
+        return ids, d2
+
+    def closest_points(self, q):
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
+        ids = np.empty(len(q), np.int32)
+        d2 = np.empty(len(q), np.float64)
+        self._ck(self.lib.vc_closest_points(self.h, _ptr(q), len(q), _ptr(ids), _ptr(d2)))
+        return ids, d2
+
+    def cell_measures_grid(self, fetch=True):
+        s = self.slab_shape
+        if fetch:
+            e, f = np.empty((3,) + s, np.float32), np.empty((3,) + s, np.float32)
+            c, r = np.empty(s, np.float32), np.empty(s, np.float32)
+        else:
+            e = f = c = r = None
+        self._ck(self.lib.vc_cell_measures_grid(self.h, _ptr(e), _ptr(f), _ptr(c), _ptr(r)))
+        return e, f, c, r
+
+    def face_lambda(self, site_pairs):
+        p = np.ascontiguousarray(site_pairs, np.int32).reshape(-1, 2)
+        out = np.empty(len(p), np.float32)
+        self._ck(self.lib.vc_face_lambda(self.h, _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def vertex_radii(self, v_xyz, site_of_v):
+        v = np.ascontiguousarray(v_xyz, np.float32).reshape(-1, 3)
+        s = np.ascontiguousarray(site_of_v, np.int32)
+        out = np.empty(len(v), np.float32)
+        self._ck(self.lib.vc_vertex_radii(self.h, _ptr(v), len(v), _ptr(s), _ptr(out)))
+        return out
+
+    def segment_max(self, off, items, value, valid=None):
+        off = np.ascontiguousarray(off, np.int32)
+        items = np.ascontiguousarray(items, np.int32)
+        value = np.ascontiguousarray(value, np.float32)
+        vv = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        out = np.empty(len(off) - 1, np.float32)
+        self._ck(self.lib.vc_segment_max(self.h, _ptr(off), _ptr(items), len(out), _ptr(value), len(value), _ptr(vv),
+                                         _ptr(out)))
+        return out
+
+    # ---- whole path
+    def run_dense(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_run_dense(self.h, C.byref(n)))
+        return n.value
+
+    def download(self, which) -> np.ndarray:
+        s = self.slab_shape
+        shape, dt = {
+            ARR_INSIDE: (s, np.uint8), ARR_ID: (s, np.int32), ARR_D2X4: (s, np.uint32),
+            ARR_EDGE3: ((3,) + s, np.float32), ARR_FACE3: ((3,) + s, np.float32),
+            ARR_CUBE: (s, np.float32), ARR_RADIUS: (s, np.float32),
+        }[which]
+        out = np.empty(shape, dt)
+        self._ck(self.lib.vc_download(self.h, which, _ptr(out)))
+        return out
+
+    def device_ptr(self, which) -> int:
+        return int(self.lib.vc_device_ptr(self.h, which) or 0)
+
+    def run_dense_host(self, vol, inside=None, ids=None, d2x4=None, edge3=None, face3=None, cube=None, radius=None) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_run_dense_host(self.h, _ptr(vol), _ptr(inside), _ptr(ids), _ptr(d2x4), _ptr(edge3),
+                                            _ptr(face3), _ptr(cube), _ptr(radius), C.byref(n)))
+        return n.value
+
+    def synchronize(self):
+        self._ck(self.lib.vc_synchronize(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.vc_stream(self.h) or 0)
+
+    # ---- instrumentation
+    def profile(self, on=True):
+        self.lib.vc_profile_enable(self.h, 1 if on else 0)
+
+    def profile_reset(self):
+        self.lib.vc_profile_reset(self.h)
+
+    def profile_report(self) -> dict:
+        out = {}
+        for i in range(self.lib.vc_profile_count(self.h)):
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+            self.lib.vc_profile_get(self.h, i, C.byref(name), C.byref(ms), C.byref(n))
+            out[name.value.decode()] = {"ms": ms.value, "launches": n.value}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.vc_launch_count(self.h))

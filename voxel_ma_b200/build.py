@@ -1,0 +1,77 @@
+"""Build libvoxcore_gpu.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc.
+
+    python -m voxel_ma_b200.build [--force]
+
+The shared library lands in voxel_ma_b200/lib/ (git-ignored, but it travels with a gpurun
+snapshot).  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libvoxcore_gpu.so")
+SOURCES = ["vc_api.cu", "vc_sites.cu", "vc_edt.cu", "vc_measures.cu", "vc_points.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # float32 measures must match the reference bit for bit: no FMA contraction
+    "-ccbin", "/usr/bin/g++",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "-Xptxas", "-v",
+]
+
+
+def _deps():
+    hdr = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdr.append(os.path.join(os.path.dirname(HERE), "include", "voxcore_gpu.h"))
+    return hdr
+
+
+def _stale(target, srcs):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def _compile(src):
+    obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+    path = os.path.join(CSRC, src)
+    if not _stale(obj, [path] + _deps()):
+        return obj, ""
+    r = subprocess.run([NVCC, *FLAGS, "-c", path, "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(_compile, SOURCES))
+    objs = [o for o, _ in res]
+    log = "".join(l for _, l in res)
+    if log:
+        with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
+            f.write(log)
+        if verbose:
+            print(log)
+    if force or _stale(LIB, objs):
+        r = subprocess.run([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

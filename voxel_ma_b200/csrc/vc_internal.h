@@ -1,0 +1,153 @@
+// vc_internal.h -- context, device buffers, launch/profile helper shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/voxcore_gpu.h"
+#include "vc_core.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return (T*)p; }
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap && p)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0)
+            bytes = 256;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess)
+            cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct KStat
+{
+    std::string name;
+    double ms = 0.0;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct vc_ctx
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // grid: global size, owned vertex planes [z0,z1), closest planes [z0,zc), resident voxel planes [zlo,zhi)
+    int nx = 0, ny = 0, nz = 0, z0 = 0, z1 = 0, zc = 0, zlo = 0, zhi = 0;
+    bool have_grid = false, have_vol = false, have_inside = false, have_sites = false, have_closest = false,
+         have_measures = false;
+    bool lattice = true; // sites lie on the corner lattice -> dense transform
+    DevBuf vol, inside;
+    // site candidates of this slab (unsorted) and the global, numbered site set
+    DevBuf cand_key, cand_corner;
+    int64_t ncand = 0;
+    DevBuf site_key, site_corner, site_xyz; // u64, u64, float4 in id order
+    int64_t nsites = 0;
+    DevBuf line_ptr, line_ent; // z-line lists: int32[(nx+1)(ny+1)+1], u64 (cz<<32|id)
+    // transform scratch + results
+    DevBuf g1, g2, id, d2, edge3, face3, cube, radius;
+    // sort scratch
+    DevBuf sk0, sk1, sv0, sv1, shist;
+    DevBuf scratch; // small device scratch (counters)
+    void* pinned = nullptr; // small pinned host scratch
+    // general (non-lattice) sites: uniform cell list
+    DevBuf cl_ptr, cl_ent, gsites; // int32 offsets, int32 site ids per cell, double3 sites
+    int cl_dim[3] = {0, 0, 0};
+    double cl_org[3] = {0, 0, 0}, cl_h = 1.0;
+    std::string err;
+    bool profiling = false;
+    std::vector<KStat> stats;
+    std::vector<cudaEvent_t> ev_pool;
+    int64_t launches = 0;
+};
+
+int vc_fail(vc_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
+
+#define VC_CUDA(c, call)                                       \
+    do                                                         \
+    {                                                          \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess)                                 \
+            return vc_fail((c), VC_ERR_CUDA, #call, _e);       \
+    } while (0)
+
+#define VC_TRY(call)          \
+    do                        \
+    {                         \
+        int _s = (call);      \
+        if (_s != VC_OK)      \
+            return _s;        \
+    } while (0)
+
+// RAII launch bracket: counts the launch and, when profiling, records CUDA events on the ctx stream
+struct ProfScope
+{
+    vc_ctx* c;
+    KStat* st = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(vc_ctx* ctx, const char* name);
+    ~ProfScope();
+};
+
+#define VC_LAUNCH(c, name, kern, grid, block, smem, ...)               \
+    do                                                                 \
+    {                                                                  \
+        ProfScope _ps((c), (name));                                    \
+        kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);   \
+    } while (0)
+
+static inline unsigned vc_blocks(size_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+static inline bool vc_is_device_ptr(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- stage functions (vc_stages.cu / vc_sites.cu / vc_edt.cu / vc_measures.cu) -------------------
+int st_classify(vc_ctx* c);
+int st_detect_sites(vc_ctx* c);
+int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key);
+int st_closest_lattice(vc_ctx* c);
+int st_measures(vc_ctx* c, bool want_radius);
+int st_classify_points(vc_ctx* c, const float* xyz, int64_t n, const double* M, uint8_t* out);
+int st_face_lambda(vc_ctx* c, const int32_t* pairs, int64_t nf, float* out);
+int st_vertex_radii(vc_ctx* c, const float* v, int64_t nv, const int32_t* site_of_v, float* out);
+int st_segment_max(vc_ctx* c, const int32_t* off, const int32_t* items, int64_t n, const float* value,
+                   int64_t nvalue, const uint8_t* valid, float* out);
+int st_upload_f64_zfast(vc_ctx* c, const double* vol);
+// general sites
+int st_build_cell_list(vc_ctx* c, const float* xyz_host, int64_t n);
+int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double* d2);
+int st_closest_general_grid(vc_ctx* c);
+
+// radix sort of (u64 key, u32 value) pairs on bits [0,nbits); result pointers returned
+int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io);

@@ -1,0 +1,323 @@
+// vc_measures.cu -- stage 3: medial measures, plus the small per-element operators of the
+// Voronoi-complex side of the boundary (tagVert, face lambda, vertex radii, max aggregation).
+//
+// Arithmetic follows the reference in float32, operation by operation, with explicit
+// round-to-nearest intrinsics so nvcc cannot contract a multiply-add into an FMA:
+//   MeasureForMA::lambdaForFace = trimesh::dist (include/measureforMA_imp.h:1-4,
+//   3rdparty/trimesh2/include/Vec.h:1128-1143):  d2 = sqr(b0-a0); d2 += sqr(b1-a1); d2 += sqr(b2-a2); sqrt.
+#include "vc_internal.h"
+
+__device__ __forceinline__ float vc_dist2f(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float t = __fsub_rn(bx, ax);
+    float d2 = __fmul_rn(t, t);
+    t = __fsub_rn(by, ay);
+    d2 = __fadd_rn(d2, __fmul_rn(t, t));
+    t = __fsub_rn(bz, az);
+    d2 = __fadd_rn(d2, __fmul_rn(t, t));
+    return d2;
+}
+
+// =============================================================================================
+// K5  dense cell measures (dictionary of SURVEY section 0).  One thread per grid vertex v; the 7
+// cells anchored at v need the sites of the 8 vertices of v's cube.  sqrt is monotone and
+// correctly rounded, so max over edges of sqrt(d2) == sqrt(max d2): the 12 edge terms are reduced
+// as squared distances and only the 7 outputs (+ radius) take a square root.
+// id: planes [z0, zc) (zc = z1+1 halo when z1 < nz); inside: planes [zlo, zhi).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+    k_cell_measures(const int* __restrict__ id, const u8* __restrict__ inside, const float4* __restrict__ site,
+                    int nx, int ny, int nz, int z0, int z1, int zc, int zlo, float* __restrict__ edge3,
+                    float* __restrict__ face3, float* __restrict__ cube, float* __restrict__ radius)
+{
+    const size_t nv = (size_t)nx * ny * (size_t)(z1 - z0);
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nv)
+        return;
+    const int x = (int)(o % nx);
+    const size_t r = o / nx;
+    const int y = (int)(r % ny);
+    const int z = z0 + (int)(r / ny);
+
+    float sx[8], sy[8], sz[8];
+    bool ok[8], in[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        int xx = x + (k & 1), yy = y + ((k >> 1) & 1), zz = z + ((k >> 2) & 1);
+        ok[k] = xx < nx && yy < ny && zz < zc;
+        in[k] = false;
+        sx[k] = sy[k] = sz[k] = 0.0f;
+        if (ok[k])
+        {
+            size_t plane = (size_t)nx * ny;
+            int sid = __ldg(id + (size_t)xx + (size_t)nx * yy + plane * (size_t)(zz - z0));
+            in[k] = __ldg(inside + (size_t)xx + (size_t)nx * yy + plane * (size_t)(zz - zlo)) != 0;
+            if (sid >= 0)
+            {
+                float4 s = __ldg(site + sid);
+                sx[k] = s.x;
+                sy[k] = s.y;
+                sz[k] = s.z;
+            }
+            else
+                ok[k] = false;
+        }
+    }
+#define E2(a, b) ((ok[a] && ok[b]) ? vc_dist2f(sx[a], sy[a], sz[a], sx[b], sy[b], sz[b]) : 0.0f)
+    // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
+    const float x0 = E2(0, 1), x1 = E2(2, 3), x2 = E2(4, 5), x3 = E2(6, 7);
+    const float y0 = E2(0, 2), y1 = E2(1, 3), y2 = E2(4, 6), y3 = E2(5, 7);
+    const float w0 = E2(0, 4), w1 = E2(1, 5), w2 = E2(2, 6), w3 = E2(3, 7);
+#undef E2
+    if (edge3)
+    {
+        __stcs(edge3 + o, (in[0] && in[1]) ? __fsqrt_rn(x0) : 0.0f);
+        __stcs(edge3 + nv + o, (in[0] && in[2]) ? __fsqrt_rn(y0) : 0.0f);
+        __stcs(edge3 + 2 * nv + o, (in[0] && in[4]) ? __fsqrt_rn(w0) : 0.0f);
+    }
+    const float fxy = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
+    const float fxz = fmaxf(fmaxf(x0, x2), fmaxf(w0, w1));
+    const float fyz = fmaxf(fmaxf(y0, y2), fmaxf(w0, w2));
+    if (face3)
+    {
+        __stcs(face3 + o, (in[0] && in[1] && in[2] && in[3]) ? __fsqrt_rn(fxy) : 0.0f);
+        __stcs(face3 + nv + o, (in[0] && in[1] && in[4] && in[5]) ? __fsqrt_rn(fxz) : 0.0f);
+        __stcs(face3 + 2 * nv + o, (in[0] && in[2] && in[4] && in[6]) ? __fsqrt_rn(fyz) : 0.0f);
+    }
+    if (cube)
+    {
+        float m = fmaxf(fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)), fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+        m = fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)));
+        bool all = in[0] && in[1] && in[2] && in[3] && in[4] && in[5] && in[6] && in[7];
+        __stcs(cube + o, all ? __fsqrt_rn(m) : 0.0f);
+    }
+    if (radius)
+        __stcs(radius + o, ok[0] ? __fsqrt_rn(vc_dist2f(sx[0], sy[0], sz[0], (float)x, (float)y, (float)z)) : 0.0f);
+}
+
+int st_measures(vc_ctx* c, bool want_radius)
+{
+    if (!c->have_closest || !c->have_inside)
+        return vc_fail(c, VC_ERR_STATE, "vc_cell_measures_grid needs vc_classify_grid and vc_closest_grid");
+    if (c->zhi < c->zc)
+        return vc_fail(c, VC_ERR_STATE, "inside flags do not cover the halo plane");
+    const size_t nv = (size_t)c->nx * c->ny * (size_t)(c->z1 - c->z0);
+    VC_CUDA(c, c->edge3.ensure(nv * 3 * 4));
+    VC_CUDA(c, c->face3.ensure(nv * 3 * 4));
+    VC_CUDA(c, c->cube.ensure(nv * 4));
+    if (want_radius)
+        VC_CUDA(c, c->radius.ensure(nv * 4));
+    VC_LAUNCH(c, "cell_measures", k_cell_measures, vc_blocks(nv, 256), 256, 0, c->id.as<int>(), c->inside.as<u8>(),
+              c->site_xyz.as<float4>(), c->nx, c->ny, c->nz, c->z0, c->z1, c->zc, c->zlo, c->edge3.as<float>(),
+              c->face3.as<float>(), c->cube.as<float>(), want_radius ? c->radius.as<float>() : nullptr);
+    VC_CUDA(c, cudaGetLastError());
+    c->have_measures = true;
+    return VC_OK;
+}
+
+// =============================================================================================
+// a4  VoroInfo::tagVert (src/voroinfo.cpp:447-454): q = M*p in double with the homogeneous divide
+// of XForm.h:479-489, cast to float, round half away from zero, bounds, flag lookup.
+// =============================================================================================
+struct Mat16
+{
+    double m[16];
+};
+
+__global__ void k_classify_points(const float* __restrict__ xyz, int64_t n, Mat16 M, const u8* __restrict__ inside,
+                                  int nx, int ny, int nz, u8* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double* xf = M.m;
+    double v0 = xyz[3 * i], v1 = xyz[3 * i + 1], v2 = xyz[3 * i + 2];
+#define ROW(a, b, cc, d) __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xf[a], v0), __dmul_rn(xf[b], v1)), __dmul_rn(xf[cc], v2)), xf[d])
+    double h = __ddiv_rn(1.0, ROW(3, 7, 11, 15));
+    float q0 = __double2float_rn(__dmul_rn(h, ROW(0, 4, 8, 12)));
+    float q1 = __double2float_rn(__dmul_rn(h, ROW(1, 5, 9, 13)));
+    float q2 = __double2float_rn(__dmul_rn(h, ROW(2, 6, 10, 14)));
+#undef ROW
+    // (int)std::round(float): half away from zero (include/spaceinfo.h:100-102)
+    int x = (int)roundf(q0), y = (int)roundf(q1), z = (int)roundf(q2);
+    bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
+    out[i] = in ? inside[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z)] : (u8)0;
+}
+
+int st_classify_points(vc_ctx* c, const float* xyz, int64_t n, const double* M, uint8_t* out)
+{
+    if (!c->have_inside)
+        return vc_fail(c, VC_ERR_STATE, "vc_classify_points needs vc_classify_grid first");
+    if (c->zlo != 0 || c->zhi != c->nz)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "vc_classify_points needs the whole grid resident");
+    if (n == 0)
+        return VC_OK;
+    Mat16 m;
+    static const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int i = 0; i < 16; ++i)
+        m.m[i] = M ? M[i] : I[i];
+    DevBuf din, dout;
+    VC_CUDA(c, din.ensure((size_t)n * 12));
+    cudaError_t e = dout.ensure((size_t)n);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(din.p, xyz, (size_t)n * 12, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "classify_points", k_classify_points, vc_blocks((size_t)n, 256), 256, 0, din.as<float>(), n, m,
+                  c->inside.as<u8>(), c->nx, c->ny, c->nz, dout.as<u8>());
+        e = cudaMemcpyAsync(out, dout.p, (size_t)n, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    din.release();
+    dout.release();
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "classify_points", e);
+    return VC_OK;
+}
+
+// =============================================================================================
+// a7 / a8 on a Voronoi complex
+// =============================================================================================
+__global__ void k_face_lambda(const float4* __restrict__ site, const int2* __restrict__ pairs, int64_t nf, int64_t ns,
+                              float* __restrict__ out)
+{
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf)
+        return;
+    int2 p = pairs[f];
+    float r = 0.0f;
+    if (p.x >= 0 && p.x < ns && p.y >= 0 && p.y < ns)
+    {
+        float4 a = __ldg(site + p.x), b = __ldg(site + p.y);
+        r = __fsqrt_rn(vc_dist2f(a.x, a.y, a.z, b.x, b.y, b.z));
+    }
+    out[f] = r;
+}
+
+__global__ void k_vertex_radii(const float4* __restrict__ site, const float* __restrict__ v, const int* __restrict__ sv,
+                               int64_t nv, int64_t ns, float* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv)
+        return;
+    int s = sv[i];
+    float r = 0.0f;
+    if (s >= 0 && s < ns)
+    {
+        float4 a = __ldg(site + s);
+        r = __fsqrt_rn(vc_dist2f(a.x, a.y, a.z, v[3 * i], v[3 * i + 1], v[3 * i + 2])); // dist(site_p, v_p)
+    }
+    out[i] = r;
+}
+
+__global__ void k_segment_max(const int* __restrict__ off, const int* __restrict__ items, int64_t n,
+                              const float* __restrict__ value, const u8* __restrict__ valid, float* __restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n)
+        return;
+    float m = 0.0f;
+    for (int k = off[e]; k < off[e + 1]; ++k)
+    {
+        int f = items[k];
+        if (valid && !valid[f])
+            continue;
+        float v = value[f];
+        m = v > m ? v : m; // std::max(m, v)
+    }
+    out[e] = m;
+}
+
+// small helper: temp device arrays for host-pointer operators
+struct Tmp
+{
+    std::vector<DevBuf> bufs;
+    ~Tmp()
+    {
+        for (auto& b : bufs)
+            b.release();
+    }
+    void* up(vc_ctx* c, const void* host, size_t bytes, cudaError_t& e)
+    {
+        bufs.emplace_back();
+        if (e == cudaSuccess)
+            e = bufs.back().ensure(bytes);
+        if (e == cudaSuccess && host)
+            e = cudaMemcpyAsync(bufs.back().p, host, bytes, cudaMemcpyDefault, c->stream);
+        return bufs.back().p;
+    }
+};
+
+int st_face_lambda(vc_ctx* c, const int32_t* pairs, int64_t nf, float* out)
+{
+    if (!c->have_sites)
+        return vc_fail(c, VC_ERR_STATE, "vc_face_lambda needs sites");
+    if (nf == 0)
+        return VC_OK;
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    int2* dp = (int2*)t.up(c, pairs, (size_t)nf * 8, e);
+    float* dout = (float*)t.up(c, nullptr, (size_t)nf * 4, e);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "face_lambda", k_face_lambda, vc_blocks((size_t)nf, 256), 256, 0, c->site_xyz.as<float4>(), dp, nf,
+                  c->nsites, dout);
+        e = cudaMemcpyAsync(out, dout, (size_t)nf * 4, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "face_lambda", e);
+    return VC_OK;
+}
+
+int st_vertex_radii(vc_ctx* c, const float* v, int64_t nv, const int32_t* site_of_v, float* out)
+{
+    if (!c->have_sites)
+        return vc_fail(c, VC_ERR_STATE, "vc_vertex_radii needs sites");
+    if (nv == 0)
+        return VC_OK;
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    float* dv = (float*)t.up(c, v, (size_t)nv * 12, e);
+    int* ds = (int*)t.up(c, site_of_v, (size_t)nv * 4, e);
+    float* dout = (float*)t.up(c, nullptr, (size_t)nv * 4, e);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "vertex_radii", k_vertex_radii, vc_blocks((size_t)nv, 256), 256, 0, c->site_xyz.as<float4>(), dv,
+                  ds, nv, c->nsites, dout);
+        e = cudaMemcpyAsync(out, dout, (size_t)nv * 4, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "vertex_radii", e);
+    return VC_OK;
+}
+
+int st_segment_max(vc_ctx* c, const int32_t* off, const int32_t* items, int64_t n, const float* value,
+                   int64_t nvalue, const uint8_t* valid, float* out)
+{
+    if (n == 0)
+        return VC_OK;
+    int32_t nitems = off[n];
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    int* doff = (int*)t.up(c, off, (size_t)(n + 1) * 4, e);
+    int* dit = (int*)t.up(c, items, (size_t)(nitems > 0 ? nitems : 1) * 4, e);
+    float* dval = (float*)t.up(c, value, (size_t)(nvalue > 0 ? nvalue : 1) * 4, e);
+    u8* dvalid = valid ? (u8*)t.up(c, valid, (size_t)(nvalue > 0 ? nvalue : 1), e) : nullptr;
+    float* dout = (float*)t.up(c, nullptr, (size_t)n * 4, e);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "segment_max", k_segment_max, vc_blocks((size_t)n, 256), 256, 0, doff, dit, n, dval, dvalid, dout);
+        e = cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "segment_max", e);
+    return VC_OK;
+}

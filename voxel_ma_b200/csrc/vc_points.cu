@@ -1,0 +1,351 @@
+// vc_points.cu -- stage 2 for arbitrary query points and arbitrary (non-lattice) site sets: the
+// drop-in for ANNkd_tree::annkSearch(q, k=1, eps=0) (3rdparty/ann/src/kd_search.cpp:88-216; call
+// sites src/voroinfo.cpp:362, src/voxelapps.cpp:217,345, src/exporters.cpp:629-636).
+//
+// Sites are binned into a uniform cell list by the device radix sort (vc_sites.cu); each query does
+// an exact expanding-shell search: ring r of cells (Chebyshev distance r from the query's cell) is
+// scanned, and the search stops once the best squared distance is strictly below (r*h)^2, the
+// least any site in an unvisited ring can have.  Arithmetic is ANN's: double, squared L2, terms
+// accumulated x,y,z (3rdparty/ann/src/ANN.cpp:43-58), no FMA contraction; ties go to the lowest
+// site id (3rdparty/ann/src/brute.cpp:56-82 -- the kd-tree returns the same distance but an
+// order-dependent id).
+#include <cmath>
+
+#include "vc_internal.h"
+
+struct CellGrid
+{
+    double org[3];
+    double h, inv_h;
+    int dim[3];
+};
+
+__device__ __forceinline__ int cg_cell(const CellGrid& g, double v, int a)
+{
+    int k = (int)floor((v - g.org[a]) * g.inv_h);
+    return k < 0 ? 0 : (k >= g.dim[a] ? g.dim[a] - 1 : k);
+}
+
+__global__ void k_cell_keys(const double* __restrict__ s, int64_t n, CellGrid g, u64* __restrict__ key, u32* __restrict__ val)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int cx = cg_cell(g, s[3 * i], 0), cy = cg_cell(g, s[3 * i + 1], 1), cz = cg_cell(g, s[3 * i + 2], 2);
+    key[i] = ((u64)cz * g.dim[1] + cy) * g.dim[0] + cx;
+    val[i] = (u32)i;
+}
+
+__global__ void k_cell_ptr(const u64* __restrict__ key_sorted, int64_t n, int64_t ncells, int* __restrict__ ptr)
+{
+    int64_t cidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx > ncells)
+        return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+        int64_t mid = (lo + hi) >> 1;
+        if (key_sorted[mid] < (u64)cidx)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    ptr[cidx] = (int)lo;
+}
+
+// sites of a cell, in ascending id order, re-packed next to each other: (x,y,z) doubles + id
+__global__ void k_cell_gather(const double* __restrict__ s, const u32* __restrict__ ids, int64_t n, double* __restrict__ packed,
+                              int* __restrict__ ent)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    u32 id = ids[i];
+    packed[3 * i] = s[3 * (size_t)id];
+    packed[3 * i + 1] = s[3 * (size_t)id + 1];
+    packed[3 * i + 2] = s[3 * (size_t)id + 2];
+    ent[i] = (int)id;
+}
+
+__device__ __forceinline__ void scan_cell(const double* __restrict__ ps, const int* __restrict__ ent, int b, int e, double q0,
+                                          double q1, double q2, double& best, int& bid)
+{
+    for (int k = b; k < e; ++k)
+    {
+        double t = __dsub_rn(q0, ps[3 * k]);
+        double d = __dmul_rn(t, t);
+        t = __dsub_rn(q1, ps[3 * k + 1]);
+        d = __dadd_rn(d, __dmul_rn(t, t));
+        t = __dsub_rn(q2, ps[3 * k + 2]);
+        d = __dadd_rn(d, __dmul_rn(t, t));
+        int id = ent[k];
+        if (d < best || (d == best && id < bid))
+        {
+            best = d;
+            bid = id;
+        }
+    }
+}
+
+// GRID = false: queries are q[3*i..]; GRID = true: query i is the grid vertex (x,y,z) of the slab.
+template <bool GRID>
+__global__ void __launch_bounds__(128)
+    k_closest_points(const double* __restrict__ q, int64_t n, CellGrid g, const int* __restrict__ ptr,
+                     const double* __restrict__ ps, const int* __restrict__ ent, int nx, int ny, int z0, int* __restrict__ id_out,
+                     double* __restrict__ d2_out, u32* __restrict__ d2x4_out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    double q0, q1, q2;
+    if (GRID)
+    {
+        q0 = (double)(i % nx);
+        int64_t r = i / nx;
+        q1 = (double)(r % ny);
+        q2 = (double)(z0 + r / ny);
+    }
+    else
+    {
+        q0 = q[3 * i];
+        q1 = q[3 * i + 1];
+        q2 = q[3 * i + 2];
+    }
+    const int c0 = cg_cell(g, q0, 0), c1 = cg_cell(g, q1, 1), c2 = cg_cell(g, q2, 2);
+    double best = INFINITY;
+    int bid = -1;
+    const int rmax = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    for (int r = 0; r <= rmax; ++r)
+    {
+        if (r > 0)
+        {
+            double lim = (double)(r - 1) * g.h; // every unvisited site is at least (r-1)*h away once ring r-1 is done
+            if (best < lim * lim * (1.0 - 1e-12))
+                break;
+        }
+        const int zl = c2 - r, zh = c2 + r, yl = c1 - r, yh = c1 + r, xl = c0 - r, xh = c0 + r;
+        for (int z = max(zl, 0); z <= min(zh, g.dim[2] - 1); ++z)
+        {
+            const bool zface = (z == zl || z == zh);
+            for (int y = max(yl, 0); y <= min(yh, g.dim[1] - 1); ++y)
+            {
+                const bool yface = (y == yl || y == yh);
+                const int64_t row = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                if (zface || yface)
+                { // the whole x-run belongs to the ring: cells are consecutive in the list
+                    int xa = max(xl, 0), xb = min(xh, g.dim[0] - 1);
+                    if (xa <= xb)
+                        scan_cell(ps, ent, ptr[row + xa], ptr[row + xb + 1], q0, q1, q2, best, bid);
+                }
+                else
+                {
+                    if (xl >= 0)
+                        scan_cell(ps, ent, ptr[row + xl], ptr[row + xl + 1], q0, q1, q2, best, bid);
+                    if (xh < g.dim[0] && r > 0)
+                        scan_cell(ps, ent, ptr[row + xh], ptr[row + xh + 1], q0, q1, q2, best, bid);
+                }
+            }
+        }
+    }
+    id_out[i] = bid;
+    if (d2_out)
+        d2_out[i] = best;
+    if (d2x4_out)
+        d2x4_out[i] = bid < 0 ? 0xFFFFFFFFu : (u32)__double2ll_rn(4.0 * best);
+}
+
+static CellGrid g_of(const vc_ctx* c)
+{
+    CellGrid g;
+    for (int a = 0; a < 3; ++a)
+    {
+        g.org[a] = c->cl_org[a];
+        g.dim[a] = c->cl_dim[a];
+    }
+    g.h = c->cl_h;
+    g.inv_h = 1.0 / c->cl_h;
+    return g;
+}
+
+// device-side cell list from the id-ordered float4 site table (lattice or external sites alike)
+static int build_from_device_sites(vc_ctx* c, const double* dsites, int64_t n, const double lo[3], const double hi[3])
+{
+    double ext[3], vol = 1.0;
+    for (int a = 0; a < 3; ++a)
+    {
+        ext[a] = hi[a] - lo[a];
+        if (ext[a] < 1e-9)
+            ext[a] = 1e-9;
+        vol *= ext[a];
+    }
+    // sites sample a surface: aim at ~2 sites per occupied cell with h ~ sqrt(area/n) ~ cbrt(vol)/sqrt(n)^(2/3)
+    double h = cbrt(vol / (double)(n > 0 ? n : 1)) * 1.5;
+    double maxext = fmax(ext[0], fmax(ext[1], ext[2]));
+    if (h < maxext / 512.0)
+        h = maxext / 512.0;
+    if (!(h > 0))
+        h = 1.0;
+    int64_t ncells = 1;
+    for (int a = 0; a < 3; ++a)
+    {
+        c->cl_org[a] = lo[a];
+        c->cl_dim[a] = (int)floor(ext[a] / h) + 1;
+        ncells *= c->cl_dim[a];
+    }
+    c->cl_h = h;
+    CellGrid g = g_of(c);
+    VC_CUDA(c, c->sk0.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->sk1.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->sv0.ensure((size_t)(n + 1) * 4));
+    VC_CUDA(c, c->sv1.ensure((size_t)(n + 1) * 4));
+    VC_CUDA(c, c->cl_ptr.ensure((size_t)(ncells + 2) * 4));
+    VC_CUDA(c, c->cl_ent.ensure((size_t)(n + 1) * 4));
+    DevBuf packed;
+    VC_CUDA(c, packed.ensure((size_t)(n + 1) * 24));
+    u64* k = c->sk0.as<u64>();
+    u32* v = c->sv0.as<u32>();
+    unsigned blocks = vc_blocks((size_t)(n > 0 ? n : 1), 256);
+    if (n)
+        VC_LAUNCH(c, "cell_keys", k_cell_keys, blocks, 256, 0, dsites, n, g, k, v);
+    int bits = 1;
+    while (bits < 62 && ((u64)ncells >> bits))
+        ++bits;
+    int s = vc_radix_sort_pairs(c, n, bits, &k, &v);
+    if (s == VC_OK)
+    {
+        VC_LAUNCH(c, "cell_ptr", k_cell_ptr, vc_blocks((size_t)ncells + 1, 256), 256, 0, k, n, ncells, c->cl_ptr.as<int>());
+        if (n)
+            VC_LAUNCH(c, "cell_gather", k_cell_gather, blocks, 256, 0, dsites, v, n, packed.as<double>(), c->cl_ent.as<int>());
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess)
+            s = vc_fail(c, VC_ERR_CUDA, "cell list", e);
+    }
+    if (s == VC_OK)
+    { // keep the cell-ordered coordinates (replace the id-ordered copy)
+        c->gsites.release();
+        c->gsites = packed;
+    }
+    else
+        packed.release();
+    return s;
+}
+
+int st_build_cell_list(vc_ctx* c, const float* xyz_host, int64_t n)
+{
+    // widen to double exactly as the reference does for ANN (src/voroinfo.cpp:336-341)
+    std::vector<double> s((size_t)n * 3);
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int64_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a)
+        {
+            double v = (double)xyz_host[3 * i + a];
+            s[3 * i + a] = v;
+            if (i == 0 || v < lo[a])
+                lo[a] = v;
+            if (i == 0 || v > hi[a])
+                hi[a] = v;
+        }
+    DevBuf ds;
+    VC_CUDA(c, ds.ensure((size_t)(n + 1) * 24));
+    if (n)
+        VC_CUDA(c, cudaMemcpyAsync(ds.p, s.data(), (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+    // id-ordered float4 table for the measure kernels
+    VC_CUDA(c, c->site_xyz.ensure((size_t)(n + 1) * 16));
+    {
+        std::vector<float> f4((size_t)n * 4, 0.0f);
+        for (int64_t i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a)
+                f4[4 * i + a] = xyz_host[3 * i + a];
+        if (n)
+            VC_CUDA(c, cudaMemcpyAsync(c->site_xyz.p, f4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    int st = build_from_device_sites(c, ds.as<double>(), n, lo, hi);
+    ds.release();
+    if (st != VC_OK)
+        return st;
+    c->nsites = n;
+    c->lattice = false;
+    c->have_sites = true;
+    c->have_closest = c->have_measures = false;
+    return VC_OK;
+}
+
+__global__ void k_sites_to_double(const float4* __restrict__ s, int64_t n, double* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float4 v = s[i];
+    out[3 * i] = (double)v.x;
+    out[3 * i + 1] = (double)v.y;
+    out[3 * i + 2] = (double)v.z;
+}
+
+// lattice sites: the cell list is built lazily the first time an arbitrary-point query arrives
+static int ensure_cell_list(vc_ctx* c)
+{
+    if (c->cl_dim[0] > 0 && c->gsites.p)
+        return VC_OK;
+    int64_t n = c->nsites;
+    DevBuf ds;
+    VC_CUDA(c, ds.ensure((size_t)(n + 1) * 24));
+    if (n)
+        VC_LAUNCH(c, "sites_to_double", k_sites_to_double, vc_blocks((size_t)n, 256), 256, 0, c->site_xyz.as<float4>(), n,
+                  ds.as<double>());
+    double lo[3] = {-0.5, -0.5, -0.5}, hi[3] = {c->nx - 0.5, c->ny - 0.5, c->nz - 0.5};
+    int st = build_from_device_sites(c, ds.as<double>(), n, lo, hi);
+    ds.release();
+    return st;
+}
+
+int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double* d2)
+{
+    if (!c->have_sites)
+        return vc_fail(c, VC_ERR_STATE, "vc_closest_points needs sites");
+    if (n == 0)
+        return VC_OK;
+    VC_TRY(ensure_cell_list(c));
+    DevBuf dq, did, dd;
+    cudaError_t e = dq.ensure((size_t)n * 24);
+    if (e == cudaSuccess)
+        e = did.ensure((size_t)n * 4);
+    if (e == cudaSuccess)
+        e = dd.ensure((size_t)n * 8);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dq.p, q, (size_t)n * 24, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "closest_points", (k_closest_points<false>), vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), n,
+                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), 0, 0, 0, did.as<int>(),
+                  dd.as<double>(), (u32*)nullptr);
+        e = cudaMemcpyAsync(id, did.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess && d2)
+            e = cudaMemcpyAsync(d2, dd.p, (size_t)n * 8, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    dq.release();
+    did.release();
+    dd.release();
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "closest_points", e);
+    return VC_OK;
+}
+
+// arbitrary (non-lattice) site set queried at every grid vertex of the slab
+int st_closest_general_grid(vc_ctx* c)
+{
+    VC_TRY(ensure_cell_list(c));
+    const int nplanes = c->zc - c->z0;
+    const size_t nv = (size_t)c->nx * c->ny * nplanes;
+    VC_CUDA(c, c->id.ensure(nv * 4));
+    VC_CUDA(c, c->d2.ensure(nv * 4));
+    VC_LAUNCH(c, "closest_grid_celllist", (k_closest_points<true>), vc_blocks(nv, 128), 128, 0, (const double*)nullptr,
+              (int64_t)nv, g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), c->nx, c->ny, c->z0,
+              c->id.as<int>(), (double*)nullptr, c->d2.as<u32>());
+    VC_CUDA(c, cudaGetLastError());
+    c->have_closest = true;
+    c->have_measures = false;
+    return VC_OK;
+}

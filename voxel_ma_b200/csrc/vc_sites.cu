@@ -1,0 +1,495 @@
+// vc_sites.cu -- stage 1 (classify) and stage 1'' (boundary samples): classification kernels,
+// per-corner site detection, the device radix sort that numbers the sites in the reference's
+// first-encounter order, and the per-z-line site lists the closest-site transform starts from.
+//
+// Replaces: SpaceConverter::get_occupancy_at_vox over all voxels (include/spaceinfo.h:122-129) and
+// Surfacer::extractBoundaryVts (src/surfacing.cpp:223-321).
+#include "vc_internal.h"
+
+// =============================================================================================
+// K1  classify: inside <=> value > 0.0  (NaN, 0, -0 are outside).  5 B / voxel: one 128-bit load,
+// one 32-bit store per 4 voxels.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_classify_f32(const float* __restrict__ vol, u8* __restrict__ inside, size_t n)
+{
+    size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i4 + 3 < n; i4 += stride)
+    {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(vol + i4));
+        uchar4 o;
+        o.x = v.x > 0.0f;
+        o.y = v.y > 0.0f;
+        o.z = v.z > 0.0f;
+        o.w = v.w > 0.0f;
+        *reinterpret_cast<uchar4*>(inside + i4) = o;
+    }
+    // tail (n not a multiple of 4): the thread that would own the last partial vector
+    if (i4 < n && i4 + 3 >= n)
+        for (size_t i = i4; i < n; ++i)
+            inside[i] = vol[i] > 0.0f;
+}
+
+// Tao's in-memory order double[x][y][z] (z fastest) -> flags [z][y][x]; 32x32 (x,z) tile per y.
+__global__ void k_classify_f64_zfast(const double* __restrict__ vol, u8* __restrict__ inside, int nx, int ny, int nz)
+{
+    __shared__ u8 tile[32][33];
+    int y = blockIdx.z;
+    int x0 = blockIdx.x * 32, zb = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    {
+        int x = x0 + r, z = zb + threadIdx.x;
+        if (x < nx && z < nz)
+            tile[r][threadIdx.x] = vol[((size_t)x * ny + y) * nz + z] > 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    {
+        int z = zb + r, x = x0 + threadIdx.x;
+        if (x < nx && z < nz)
+            inside[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z)] = tile[threadIdx.x][r];
+    }
+}
+
+int st_classify(vc_ctx* c)
+{
+    if (!c->have_vol)
+        return vc_fail(c, VC_ERR_STATE, "vc_classify_grid: no volume uploaded");
+    size_t n = (size_t)c->nx * c->ny * (size_t)(c->zhi - c->zlo);
+    VC_CUDA(c, c->inside.ensure(n + 16));
+    size_t want = (n / 4 + 255) / 256 + 1, cap = (size_t)c->sm_count * 16;
+    unsigned blocks = (unsigned)(want < cap ? want : cap);
+    VC_LAUNCH(c, "classify_f32", k_classify_f32, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(), n);
+    VC_CUDA(c, cudaGetLastError());
+    c->have_inside = true;
+    c->have_sites = c->have_closest = c->have_measures = false;
+    return VC_OK;
+}
+
+int st_upload_f64_zfast(vc_ctx* c, const double* vol)
+{
+    if (!c->have_grid || c->z0 != 0 || c->z1 != c->nz)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "vc_volume_upload_f64_zfast needs a ctx that owns the whole grid");
+    size_t n = (size_t)c->nx * c->ny * c->nz;
+    DevBuf tmp;
+    VC_CUDA(c, tmp.ensure(n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(tmp.p, vol, n * sizeof(double), cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess)
+        e = c->inside.ensure(n + 16);
+    if (e != cudaSuccess)
+    {
+        tmp.release();
+        return vc_fail(c, VC_ERR_CUDA, "upload f64", e);
+    }
+    c->zlo = 0;
+    c->zhi = c->nz;
+    dim3 grid((c->nx + 31) / 32, (c->nz + 31) / 32, c->ny), block(32, 8);
+    VC_LAUNCH(c, "classify_f64_zfast", k_classify_f64_zfast, grid, block, 0, tmp.as<double>(), c->inside.as<u8>(),
+              c->nx, c->ny, c->nz);
+    e = cudaStreamSynchronize(c->stream);
+    tmp.release();
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "classify f64", e);
+    c->have_vol = false; // only the flags are kept for a double volume
+    c->have_inside = true;
+    c->have_sites = c->have_closest = c->have_measures = false;
+    return VC_OK;
+}
+
+// =============================================================================================
+// K2  site detection: one thread per corner of the slab's corner planes [czb,cze).  A corner is a
+// site iff its 8 incident voxels (out of bounds = 0) are not all equal; its first-encounter key
+// comes from vc_site_key.  Warp-aggregated append; the order of the appended records does not
+// matter because the keys are unique and sorted afterwards.
+// =============================================================================================
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+    k_detect_sites(const u8* __restrict__ inside, int nx, int ny, int nz, int zlo, int czb, int cze,
+                   u64* __restrict__ keys, u64* __restrict__ corners, u64* __restrict__ counter)
+{
+    const int CX = nx + 1, CY = ny + 1;
+    size_t total = (size_t)CX * CY * (size_t)(cze - czb);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 key = VC_INF;
+    int cx = 0, cy = 0, cz = 0;
+    if (i < total)
+    {
+        cx = (int)(i % CX);
+        size_t r = i / CX;
+        cy = (int)(r % CY);
+        cz = czb + (int)(r / CY);
+        u32 occ = 0, inb = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit)
+        {
+            int x = cx - 1 + (bit >> 2), y = cy - 1 + ((bit >> 1) & 1), z = cz - 1 + (bit & 1);
+            bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
+            u32 o = 0;
+            if (in)
+                o = __ldg(inside + (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)(z - zlo))) ? 1u : 0u;
+            occ |= o << bit;
+            inb |= (in ? 1u : 0u) << bit;
+        }
+        key = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
+    }
+    bool is = key != VC_INF;
+    unsigned m = __ballot_sync(0xffffffffu, is);
+    if (m == 0)
+        return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    u64 base = 0;
+    if (lane == leader)
+        base = atomicAdd(counter, (u64)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (EMIT && is)
+    {
+        u64 pos = base + __popc(m & ((1u << lane) - 1));
+        keys[pos] = key;
+        corners[pos] = vc_pack_corner(cx, cy, cz);
+    }
+}
+
+int st_detect_sites(vc_ctx* c)
+{
+    if (!c->have_inside)
+        return vc_fail(c, VC_ERR_STATE, "site extraction needs vc_classify_grid first");
+    // corner planes owned by this slab: [z0,z1) plus the top plane nz for the last slab
+    int czb = c->z0, cze = (c->z1 == c->nz) ? c->nz + 1 : c->z1;
+    if (c->zlo > (czb > 0 ? czb - 1 : 0) || c->zhi < (cze - 1 < c->nz ? cze : c->nz))
+        return vc_fail(c, VC_ERR_STATE, "resident voxel planes do not cover the slab's corner planes");
+    size_t total = (size_t)(c->nx + 1) * (c->ny + 1) * (size_t)(cze - czb);
+    VC_CUDA(c, c->scratch.ensure(256));
+    u64* counter = c->scratch.as<u64>();
+    VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+    unsigned blocks = vc_blocks(total, 256);
+    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<false>, blocks, 256, 0, c->inside.as<u8>(), c->nx, c->ny, c->nz,
+              c->zlo, czb, cze, nullptr, nullptr, counter);
+    u64 n = 0;
+    VC_CUDA(c, cudaMemcpyAsync(&n, counter, 8, cudaMemcpyDeviceToHost, c->stream));
+    VC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ncand = (int64_t)n;
+    VC_CUDA(c, c->cand_key.ensure((n + 1) * 8));
+    VC_CUDA(c, c->cand_corner.ensure((n + 1) * 8));
+    if (n)
+    {
+        VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+        VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<true>, blocks, 256, 0, c->inside.as<u8>(), c->nx, c->ny,
+                  c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter);
+        VC_CUDA(c, cudaGetLastError());
+    }
+    return VC_OK;
+}
+
+// =============================================================================================
+// Device radix sort, LSD, 8 bits per pass, stable.  Tile = 256 threads x RS_ITEMS keys.
+//   histogram  -> per-(digit, tile) counts, digit-major
+//   scan       -> exclusive prefix over that table (one block)
+//   scatter    -> per-warp match_any ranking keeps the order (warp, item, lane) = index order
+// =============================================================================================
+#define RS_ITEMS 16
+#define RS_TILE (256 * RS_ITEMS)
+
+__global__ void __launch_bounds__(256) k_rs_hist(const u64* __restrict__ keys, int64_t n, int shift, u32* __restrict__ ghist, int ntiles)
+{
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    for (int i = 0; i < RS_ITEMS; ++i)
+    {
+        int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
+        if (idx < n)
+            atomicAdd(&h[(u32)(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    ghist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `len` u32 values in place, single block of 1024 threads
+__global__ void __launch_bounds__(1024) k_rs_scan(u32* __restrict__ a, int64_t len)
+{
+    __shared__ u32 wsum[32];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    const int PER = 4;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < len; base += 1024 * PER)
+    {
+        int64_t i0 = base + (int64_t)threadIdx.x * PER;
+        u32 v[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            v[k] = (i0 + k < len) ? a[i0 + k] : 0u;
+            s += v[k];
+        }
+        u32 inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += t;
+        }
+        if (lane == 31)
+            wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            u32 w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o)
+                    wi += t;
+            }
+            wsum[lane] = wi - w; // exclusive
+        }
+        __syncthreads();
+        u32 excl = carry + wsum[warp] + inc - s;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            if (i0 + k < len)
+                a[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            carry = excl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_rs_scatter(const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
+                 u32* __restrict__ vout, const u32* __restrict__ goff, int64_t n, int shift, int ntiles)
+{
+    __shared__ u32 wcnt[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256)
+        (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+    u64 k[RS_ITEMS];
+    u32 rk[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i)
+    {
+        int64_t idx = base + (int64_t)i * 32 + lane;
+        bool valid = idx < n;
+        k[i] = valid ? kin[idx] : 0ull;
+        u32 d = (u32)(k[i] >> shift) & 255u;
+        unsigned m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+        int leader = __ffs(m) - 1;
+        u32 old = 0;
+        if (valid && lane == leader)
+        {
+            old = wcnt[warp][d];
+            wcnt[warp][d] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rk[i] = old + __popc(m & ((1u << lane) - 1));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        int d = threadIdx.x;
+        u32 run = goff[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+        {
+            u32 cc = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += cc;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i)
+    {
+        int64_t idx = base + (int64_t)i * 32 + lane;
+        if (idx < n)
+        {
+            u32 d = (u32)(k[i] >> shift) & 255u;
+            u32 pos = wcnt[warp][d] + rk[i];
+            kout[pos] = k[i];
+            vout[pos] = vin[idx];
+        }
+    }
+}
+
+// note: the histogram kernel tiles by (item, thread) and the scatter by (warp, item, lane); both
+// cover exactly [tile*RS_TILE, (tile+1)*RS_TILE), which is all the per-tile counts depend on.
+int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io)
+{
+    if (n <= 1)
+        return VC_OK;
+    if (n >= (int64_t)1 << 31)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "radix sort: more than 2^31 records");
+    int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    VC_CUDA(c, c->shist.ensure((size_t)256 * ntiles * sizeof(u32)));
+    u64* kin = *keys_io;
+    u32* vin = *vals_io;
+    u64* kout = (kin == c->sk0.as<u64>()) ? c->sk1.as<u64>() : c->sk0.as<u64>();
+    u32* vout = (vin == c->sv0.as<u32>()) ? c->sv1.as<u32>() : c->sv0.as<u32>();
+    for (int shift = 0; shift < nbits; shift += 8)
+    {
+        VC_LAUNCH(c, "radix_hist", k_rs_hist, ntiles, 256, 0, kin, n, shift, c->shist.as<u32>(), ntiles);
+        VC_LAUNCH(c, "radix_scan", k_rs_scan, 1, 1024, 0, c->shist.as<u32>(), (int64_t)256 * ntiles);
+        VC_LAUNCH(c, "radix_scatter", k_rs_scatter, ntiles, 256, 0, kin, vin, kout, vout, c->shist.as<u32>(), n,
+                  shift, ntiles);
+        u64* tk = kin;
+        kin = kout;
+        kout = tk;
+        u32* tv = vin;
+        vin = vout;
+        vout = tv;
+    }
+    VC_CUDA(c, cudaGetLastError());
+    *keys_io = kin;
+    *vals_io = vin;
+    return VC_OK;
+}
+
+// =============================================================================================
+// finalize: number the sites (sort by first-encounter key), build id-ordered tables and the
+// per-z-line lists (line = cx*(ny+1)+cy, entries (cz<<32|id) ascending in cz).
+// =============================================================================================
+__global__ void k_iota_copy(const u64* __restrict__ kin, u64* __restrict__ kout, u32* __restrict__ v, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        kout[i] = kin[i];
+        v[i] = (u32)i;
+    }
+}
+
+// site tables in id order + the second sort's keys: key2 = line*(nz+1)+cz, value = id
+__global__ void k_site_tables(const u32* __restrict__ order, const u64* __restrict__ corners_in, const u64* __restrict__ keys_sorted,
+                              u64* __restrict__ site_key, u64* __restrict__ site_corner, float4* __restrict__ site_xyz,
+                              u64* __restrict__ key2, u32* __restrict__ val2, int64_t n, int ny, int nz)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    u64 pc = corners_in[order ? order[i] : i];
+    int cx, cy, cz;
+    vc_unpack_corner(pc, cx, cy, cz);
+    if (site_key)
+        site_key[i] = keys_sorted ? keys_sorted[i] : (u64)i;
+    site_corner[i] = pc;
+    site_xyz[i] = make_float4((float)cx - 0.5f, (float)cy - 0.5f, (float)cz - 0.5f, 0.0f);
+    key2[i] = ((u64)cx * (u64)(ny + 1) + (u64)cy) * (u64)(nz + 1) + (u64)cz;
+    val2[i] = (u32)i;
+}
+
+__global__ void k_line_entries(const u64* __restrict__ key2_sorted, const u32* __restrict__ ids, u64* __restrict__ ent,
+                               int64_t n, int nz)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        ent[i] = ((key2_sorted[i] % (u64)(nz + 1)) << 32) | ids[i];
+}
+
+// line_ptr[l] = first sorted position whose line >= l  (binary search per line)
+__global__ void k_line_ptr(const u64* __restrict__ key2_sorted, int64_t n, int nlines, int nz, int* __restrict__ line_ptr)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > nlines)
+        return;
+    u64 want = (u64)l * (u64)(nz + 1);
+    int64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+        int64_t mid = (lo + hi) >> 1;
+        if (key2_sorted[mid] < want)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    line_ptr[l] = (int)lo;
+}
+
+// number of adjacent equal keys in a sorted array (duplicate detection for external site sets)
+__global__ void k_count_dups(const u64* __restrict__ k, int64_t n, u64* counter)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && k[i] == k[i + 1])
+        atomicAdd(counter, 1ull);
+}
+
+static int bits_for(u64 maxval)
+{
+    int b = 1;
+    while (b < 64 && (maxval >> b))
+        ++b;
+    return b;
+}
+
+int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key)
+{
+    const int nlines = (c->nx + 1) * (c->ny + 1);
+    c->nsites = n;
+    c->lattice = true;
+    c->cl_dim[0] = 0; // any cell list of a previous site set is stale
+    VC_CUDA(c, c->site_key.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->site_corner.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->site_xyz.ensure((size_t)(n + 1) * 16));
+    VC_CUDA(c, c->line_ent.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->line_ptr.ensure((size_t)(nlines + 2) * 4));
+    VC_CUDA(c, c->sk0.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->sk1.ensure((size_t)(n + 1) * 8));
+    VC_CUDA(c, c->sv0.ensure((size_t)(n + 1) * 4));
+    VC_CUDA(c, c->sv1.ensure((size_t)(n + 1) * 4));
+    if (n == 0)
+    {
+        VC_CUDA(c, cudaMemsetAsync(c->line_ptr.p, 0, (size_t)(nlines + 2) * 4, c->stream));
+        c->have_sites = true;
+        c->have_closest = c->have_measures = false;
+        return VC_OK;
+    }
+    unsigned blocks = vc_blocks((size_t)n, 256);
+    u64* k = c->sk0.as<u64>();
+    u32* v = c->sv0.as<u32>();
+    const u32* order = nullptr;
+    const u64* ksorted = nullptr;
+    if (sort_by_key)
+    {
+        VC_LAUNCH(c, "sites_iota", k_iota_copy, blocks, 256, 0, keys_dev, k, v, n);
+        u64 maxkey = ((u64)c->nx * c->ny * c->nz) * 24ull;
+        VC_TRY(vc_radix_sort_pairs(c, n, bits_for(maxkey), &k, &v));
+        order = v;
+        ksorted = k;
+    }
+    // key2/val2 go to the buffers the first sort is NOT currently holding its result in
+    u64* k2 = (k == c->sk0.as<u64>()) ? c->sk1.as<u64>() : c->sk0.as<u64>();
+    u32* v2 = (v == c->sv0.as<u32>()) ? c->sv1.as<u32>() : c->sv0.as<u32>();
+    VC_LAUNCH(c, "site_tables", k_site_tables, blocks, 256, 0, order, corners_dev, ksorted, c->site_key.as<u64>(),
+              c->site_corner.as<u64>(), c->site_xyz.as<float4>(), k2, v2, n, c->ny, c->nz);
+    u64 maxkey2 = (u64)nlines * (u64)(c->nz + 1);
+    VC_TRY(vc_radix_sort_pairs(c, n, bits_for(maxkey2), &k2, &v2));
+    VC_LAUNCH(c, "line_entries", k_line_entries, blocks, 256, 0, k2, v2, c->line_ent.as<u64>(), n, c->nz);
+    VC_LAUNCH(c, "line_ptr", k_line_ptr, vc_blocks((size_t)nlines + 1, 256), 256, 0, k2, n, nlines, c->nz,
+              c->line_ptr.as<int>());
+    if (!sort_by_key)
+    { // external set: duplicates on the lattice would need the lowest-id rule inside a list entry
+        u64* counter = c->scratch.as<u64>();
+        VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+        VC_LAUNCH(c, "count_dups", k_count_dups, blocks, 256, 0, k2, n, counter);
+        u64 d = 0;
+        VC_CUDA(c, cudaMemcpyAsync(&d, counter, 8, cudaMemcpyDeviceToHost, c->stream));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (d)
+            c->lattice = false;
+    }
+    VC_CUDA(c, cudaGetLastError());
+    c->have_sites = true;
+    c->have_closest = c->have_measures = false;
+    return VC_OK;
+}
