@@ -87,6 +87,7 @@ def ref():
         lib = C.CDLL(REF_SO)
         lib.ref_set_data_dir.argtypes = [C.c_char_p]
         lib.ref_set_data_dir(os.path.join(HERE, "_ref").encode())
+        lib.ref_last_seconds.restype = C.c_double
         lib.ref_classify_grid.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _u8p]
         lib.ref_tag_points.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int64, _u8p]
         lib.ref_extract_sites.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]

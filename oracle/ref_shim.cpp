@@ -15,6 +15,7 @@
 #include <memory>
 #include <vector>
 #include <unistd.h>
+#include <chrono>
 
 #include <ANN/ANN.h>
 #include <isosurface/volume.h>
@@ -58,6 +59,17 @@ struct CwdGuard
 };
 
 char g_data_dir[4096] = ".";
+// seconds spent inside the reference call proper (marshalling excluded), std::chrono like the
+// reference's own struct timer (include/commondefs.h:110-168)
+double g_last_seconds = 0.0;
+struct Stopwatch
+{
+    std::chrono::high_resolution_clock::time_point t0 = std::chrono::high_resolution_clock::now();
+    ~Stopwatch()
+    {
+        g_last_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+};
 
 // gives the shim read access to VoroInfo's protected state without touching the reference
 struct VoroProbe : public voxelvoro::VoroInfo
@@ -88,6 +100,7 @@ extern "C"
 {
     // directory that holds cycle8.txt (oracle/_ref)
     void ref_set_data_dir(const char* dir) { snprintf(g_data_dir, sizeof g_data_dir, "%s", dir); }
+    double ref_last_seconds(void) { return g_last_seconds; }
 
     // a2: SpaceConverter::voxTaggedAsInside for every voxel (include/spaceinfo.h:53-58).
     // out is x-fastest: out[x + nx*(y + ny*z)].
@@ -120,8 +133,11 @@ extern "C"
         CwdGuard g(g_data_dir);
         Surfacer surf;
         vector<point> sites;
-        if (surf.extractBoundaryVts(vol, sites) != SurfacerErrCode::SUCCESS)
-            return -1;
+        {
+            Stopwatch sw;
+            if (surf.extractBoundaryVts(vol, sites) != SurfacerErrCode::SUCCESS)
+                return -1;
+        }
         int64_t n = (int64_t)sites.size();
         for (int64_t i = 0; i < n && i < cap; ++i)
         {
@@ -142,6 +158,7 @@ extern "C"
             for (int d = 0; d < dim; ++d)
                 pa[i][d] = data[(size_t)i * dim + d];
         {
+            Stopwatch sw; // tree build + queries, as the reference pays for both (src/voroinfo.cpp:344-362)
             ANNkd_tree tree(pa, n, dim);
             ANNpoint qq = annAllocPt(dim);
             for (int64_t i = 0; i < nq; ++i)

@@ -105,4 +105,47 @@ extern "C"
     }
 
     int hh_floor_div(int a, int b) { return vc_floor_div(a, b); }
+    int hh_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk) { return vc_sep(pi, Hi, pk, Hk); }
+
+    // one line of the transform on caller data (robustness tests with 2048-scale coordinates)
+    void hh_envelope(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
+    {
+        std::vector<vc_u64> stH(ncand + 1);
+        std::vector<uint32_t> stPT(ncand + 1);
+        vc_envelope_line(in, 1L, ncand, ntgt, stH.data(), stPT.data(), [&](int t, vc_u64 v) { out[t] = v; });
+    }
+
+    // (key, corner) records of one z-slab, as vc_sites_detect_local reports them: corner planes
+    // [czb,cze) of a grid nx*ny*nz; `inside` holds voxel planes [zlo, zhi). Returns the count.
+    int64_t hh_site_records(const uint8_t* inside, int nx, int ny, int nz, int zlo, int zhi, int czb, int cze,
+                            vc_u64* keys, vc_u64* corners, int64_t cap)
+    {
+        int64_t n = 0;
+        for (int cz = czb; cz < cze; ++cz)
+            for (int cy = 0; cy <= ny; ++cy)
+                for (int cx = 0; cx <= nx; ++cx)
+                {
+                    uint32_t occ = 0, inb = 0;
+                    for (int bit = 0; bit < 8; ++bit)
+                    {
+                        int x = cx - 1 + (bit >> 2), y = cy - 1 + ((bit >> 1) & 1), z = cz - 1 + (bit & 1);
+                        bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
+                        if (in && (z < zlo || z >= zhi))
+                            return -1; // slab does not hold a plane it needs
+                        uint32_t o = in ? (inside[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (z - zlo))] ? 1u : 0u) : 0u;
+                        occ |= o << bit;
+                        inb |= (in ? 1u : 0u) << bit;
+                    }
+                    vc_u64 k = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
+                    if (k == VC_INF)
+                        continue;
+                    if (n < cap)
+                    {
+                        keys[n] = k;
+                        corners[n] = vc_pack_corner(cx, cy, cz);
+                    }
+                    ++n;
+                }
+        return n;
+    }
 }

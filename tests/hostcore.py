@@ -1,0 +1,66 @@
+"""ctypes access to tests/host_harness.cpp (the kernels' integer core driven on the CPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libhostharness.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(HERE, "host_harness.cpp")
+        hdr = os.path.join(HERE, "..", "voxel_ma_b200", "csrc", "vc_core.h")
+        if (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            os.makedirs(os.path.dirname(SO), exist_ok=True)
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
+        L = C.CDLL(SO)
+        L.hh_sites.restype = C.c_int64
+        L.hh_site_records.restype = C.c_int64
+        L.hh_sep.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def sites(inside):
+    nz, ny, nx = inside.shape
+    ins = np.ascontiguousarray(inside, np.uint8)
+    n = lib().hh_sites(_p(ins), nx, ny, nz, None, C.c_int64(0))
+    out = np.empty((n, 3), np.float32)
+    lib().hh_sites(_p(ins), nx, ny, nz, _p(out), C.c_int64(n))
+    return out
+
+
+def closest_grid(sites_xyz, nx, ny, nz, z0=0, z1=None):
+    z1 = nz if z1 is None else z1
+    c = np.ascontiguousarray(np.round(np.asarray(sites_xyz) + 0.5).astype(np.int32))
+    ids = np.empty((z1 - z0, ny, nx), np.int32)
+    d2 = np.empty((z1 - z0, ny, nx), np.uint32)
+    lib().hh_closest_grid(_p(c), C.c_int64(len(c)), nx, ny, nz, z0, z1, _p(ids), _p(d2))
+    return ids, d2
+
+
+def envelope(H, ntgt):
+    H = np.ascontiguousarray(H, np.uint64)
+    out = np.empty(ntgt, np.uint64)
+    lib().hh_envelope(_p(H), len(H), ntgt, _p(out))
+    return out
+
+
+def site_records(inside_planes, nx, ny, nz, zlo, czb, cze):
+    ins = np.ascontiguousarray(inside_planes, np.uint8)
+    zhi = zlo + ins.shape[0]
+    n = lib().hh_site_records(_p(ins), nx, ny, nz, zlo, zhi, czb, cze, None, None, C.c_int64(0))
+    assert n >= 0, "slab does not hold a needed plane"
+    k = np.empty(n, np.uint64)
+    c = np.empty(n, np.uint64)
+    lib().hh_site_records(_p(ins), nx, ny, nz, zlo, zhi, czb, cze, _p(k), _p(c), C.c_int64(n))
+    return k, c

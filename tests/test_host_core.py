@@ -1,0 +1,67 @@
+"""The kernels' exact-integer core (voxel_ma_b200/csrc/vc_core.h), driven line by line on the CPU
+through tests/host_harness.cpp and compared with the oracle -- runs without a GPU."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from tests import hostcore as hc
+from tests.cases import small_cases
+
+CASES = small_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_site_numbering_matches_reference_order(name):
+    inside = ob.classify_grid(CASES[name])
+    assert np.array_equal(hc.sites(inside), ob.extract_sites(inside))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_separable_transform_is_exact(name):
+    vol = CASES[name]
+    nz, ny, nx = vol.shape
+    sites = ob.extract_sites(ob.classify_grid(vol))
+    if len(sites) == 0:
+        pytest.skip("no boundary")
+    ids, d2 = hc.closest_grid(sites, nx, ny, nz)
+    o_ids, o_d2 = ob.closest_grid(sites, nx, ny, nz)
+    assert np.array_equal(d2, o_d2) and np.array_equal(ids, o_ids)
+    if nz > 6:
+        ids2, d22 = hc.closest_grid(sites, nx, ny, nz, 2, nz - 3)
+        assert np.array_equal(ids2, o_ids[2:nz - 3]) and np.array_equal(d22, o_d2[2:nz - 3])
+
+
+def _brute_line(H, ntgt):
+    p = np.arange(len(H), dtype=np.int64)[None, :]
+    t = np.arange(ntgt, dtype=np.int64)[:, None]
+    d = 2 * (t - p) + 1
+    val = (H[None, :] >> np.uint64(32)).astype(np.int64) + d * d
+    key = (val.astype(np.uint64) << np.uint64(32)) | (H[None, :] & np.uint64(0xFFFFFFFF))
+    key = np.where(H[None, :] == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFFFFFFFFFF), key)
+    return key.min(axis=1)
+
+
+@pytest.mark.parametrize("n,dmax,density", [(7, 10, 1.0), (64, 50, 0.5), (513, 3_000_000, 0.3), (2049, 33_000_000, 0.7),
+                                            (2049, 8, 1.0), (1025, 12_000_000, 0.02), (300, 0, 1.0)])
+def test_envelope_line_random(n, dmax, density):
+    """single lines with distances up to the 2048^3 range, dense ties (equal D, distinct ids)"""
+    rng = np.random.default_rng(n * 7 + dmax % 97)
+    for rep in range(6):
+        D = (rng.integers(0, dmax + 1, size=n).astype(np.uint64) // np.uint64(8)) * np.uint64(8) + np.uint64(1)
+        ids = rng.permutation(5_000_000)[:n].astype(np.uint64)
+        H = (D << np.uint64(32)) | ids
+        H[rng.random(n) > density] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        out = hc.envelope(H, n - 1)
+        assert np.array_equal(out, _brute_line(H, n - 1))
+    empty = np.full(n, 0xFFFFFFFFFFFFFFFF, np.uint64)
+    assert (hc.envelope(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+
+
+def test_floor_div_exact():
+    rng = np.random.default_rng(0)
+    L = hc.lib()
+    for num, den in zip(rng.integers(-60_000_000, 60_000_000, 20000), rng.integers(1, 8200, 20000)):
+        assert L.hh_floor_div(int(num), int(den)) == int(num) // int(den)
+    for num in (-1, 0, 1, -8192, 8191, 50_331_648, -50_331_648):
+        for den in (1, 4, 8188, 8192):
+            assert L.hh_floor_div(num, den) == num // den

@@ -1,0 +1,63 @@
+"""Host-side z-slab logic for the multi-GPU path (one process per GPU).
+
+The grid is cut into contiguous z-slabs; every rank classifies and searches its slab plus one halo
+plane (recomputed, never exchanged).  The only exchange on the data path is the boundary-sample
+list: each rank detects the site corners of its own corner planes, the (key, corner) records are
+all-gathered (variable length), and every rank sorts the union identically, so site ids agree
+everywhere.  Works on NCCL (CUDA tensors, GPU box) and on gloo (CPU tensors, unit tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_bounds(nz: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, near-equal split of the nz grid-vertex planes; earlier ranks take the remainder."""
+    if not (0 <= rank < world) or world > nz:
+        raise ValueError(f"bad slab request: nz={nz} world={world} rank={rank}")
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+def resident_planes(z0: int, z1: int, nz: int) -> tuple[int, int]:
+    """Voxel planes a slab needs resident: its own planes plus one halo plane on each interior side
+    (the lower one feeds the slab's first corner plane, the upper one the cells that reach up)."""
+    return max(z0 - 1, 0), min(z1 + 1, nz)
+
+
+def owned_corner_planes(z0: int, z1: int, nz: int) -> tuple[int, int]:
+    """Corner planes whose sites this slab reports: [z0, z1), plus the top plane nz for the last slab."""
+    return z0, (nz + 1 if z1 == nz else z1)
+
+
+def exchange_site_records(keys, corners, group=None):
+    """All-gather variable-length (key, corner) uint64 records over torch.distributed.
+
+    keys / corners: 1-D torch int64 tensors (uint64 bit patterns) on the backend's device.  Returns
+    the concatenation over ranks in rank order (any order would do: the keys are unique and the
+    import sorts them)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    pad = torch.zeros(2, cap, dtype=torch.int64, device=keys.device)
+    pad[0, : keys.numel()] = keys
+    pad[1, : corners.numel()] = corners
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    all_keys = torch.cat([b[0, :c] for b, c in zip(bufs, counts)])
+    all_corners = torch.cat([b[1, :c] for b, c in zip(bufs, counts)])
+    return all_keys.contiguous(), all_corners.contiguous()
+
+
+def unpack_corners(corners_u64: np.ndarray) -> np.ndarray:
+    """corner record cx | cy<<21 | cz<<42  ->  int32 (n,3)."""
+    c = np.asarray(corners_u64, np.uint64)
+    m = np.uint64(0x1FFFFF)
+    return np.stack([(c & m), ((c >> np.uint64(21)) & m), ((c >> np.uint64(42)) & m)], -1).astype(np.int32)

@@ -83,21 +83,26 @@ def twist(n: int = 512, z0=None, z1=None) -> np.ndarray:
     return np.broadcast_to(f, (f.shape[0], f.shape[1], f.shape[2])).astype(np.float32)
 
 
-def assembly(n: int = 1024, count: int = 64, seed: int = 20181, z0=None, z1=None) -> np.ndarray:
+def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None) -> np.ndarray:
     """Union of `count` solids (spheres, tori, boxes) with centres / radii drawn from
-    mt19937_64(seed).  Built solid by solid on each solid's bounding box only."""
+    mt19937(seed).  ``n`` is a side length or an (nx, ny, nz) triple; solids are placed in the unit
+    cube and scaled per axis extent, sized by the smallest side.  Built solid by solid on each
+    solid's bounding box only, so a rank can generate just its own z-slab."""
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    m = min(nx, ny, nz)
     rng = np.random.Generator(np.random.MT19937(seed))  # mt19937; seeded deterministically
     nz0 = 0 if z0 is None else z0
-    nz1 = n if z1 is None else z1
-    out = np.full((nz1 - nz0, n, n), -1.0, dtype=np.float32)
+    nz1 = nz if z1 is None else z1
+    out = np.full((nz1 - nz0, ny, nx), -1.0, dtype=np.float32)
+    dims = np.array([nx, ny, nz], dtype=np.float64)
     for _ in range(count):
         kind = int(rng.integers(0, 3))
-        c = rng.uniform(0.12 * n, 0.88 * n, size=3).astype(np.float32)
-        r = np.float32(rng.uniform(0.03 * n, 0.10 * n))
+        c = (rng.uniform(0.12, 0.88, size=3) * dims).astype(np.float32)
+        r = np.float32(rng.uniform(0.03 * m, 0.10 * m))
         r2 = np.float32(rng.uniform(0.3, 0.5)) * r
         ext = int(np.ceil(r + r2 + 2))
         lo = np.maximum(np.floor(c).astype(int) - ext, 0)
-        hi = np.minimum(np.floor(c).astype(int) + ext + 1, n)
+        hi = np.minimum(np.floor(c).astype(int) + ext + 1, [nx, ny, nz])
         zlo, zhi = max(lo[2], nz0), min(hi[2], nz1)
         if zlo >= zhi:
             continue
@@ -125,8 +130,9 @@ WORKLOADS = {
 }
 
 
-def make(name: str, n: int | None = None, z0=None, z1=None) -> np.ndarray:
-    """Build a named workload, optionally at another resolution ``n`` (same shape family)."""
+def make(name: str, n=None, z0=None, z1=None) -> np.ndarray:
+    """Build a named workload, optionally at another resolution ``n`` (same shape family; the
+    assembly family also takes an (nx, ny, nz) triple)."""
     fam = name.rstrip("0123456789")
     if n is None:
         return WORKLOADS[name](z0, z1)
@@ -137,7 +143,11 @@ def make(name: str, n: int | None = None, z0=None, z1=None) -> np.ndarray:
     if fam == "twist":
         return twist(n, z0, z1)
     if fam in ("assembly", "stress"):
-        return assembly(n, count=64 if fam == "assembly" else 160, z0=z0, z1=z1)
+        m = n if np.isscalar(n) else min(n)
+        cnt = 64 if fam == "assembly" else 160
+        if not np.isscalar(n):  # keep the solid density of the cubic workload
+            cnt = max(1, int(round(cnt * (n[0] * n[1] * n[2]) / float(max(n)) ** 3)))
+        return assembly(n, count=cnt, z0=z0, z1=z1)
     raise KeyError(name)
 
 
