@@ -78,57 +78,97 @@ VC_HD int vc_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk)
 // top lives in registers (Hs,ps,ts = word, position, first target it wins); the part below the
 // top lives in stH/stPT (thread-local memory on the device).  The backward scan emits targets
 // ntgt-1 .. 0 through `emit(t, value)`.
+//
+// The candidates are fetched VC_PF at a time into two register banks that alternate: while one
+// bank is consumed the loads of the next are already in flight, so a thread keeps up to 2*VC_PF
+// independent 8-byte loads outstanding instead of one (the scan itself is a dependent chain).
+#define VC_PF 8
+
+#if defined(__CUDA_ARCH__)
+#define VC_LOAD_STREAM(p) __ldcs(p) // read once: evict-first
+#else
+#define VC_LOAD_STREAM(p) (*(p))
+#endif
+
+struct vc_env_state
+{
+    int q;
+    vc_u64 Hs;
+    int ps, ts;
+};
+
+VC_HD void vc_env_push(vc_env_state& s, vc_u64 H, int j, int ntgt, vc_u64* stH, uint32_t* stPT)
+{
+    if (H == VC_INF)
+        return;
+    while (s.q >= 0)
+    {
+        if (vc_eval(s.Hs, s.ps, s.ts) > vc_eval(H, j, s.ts))
+        { // the top loses already where its interval starts: it wins nowhere
+            --s.q;
+            if (s.q >= 0)
+            {
+                s.Hs = stH[s.q];
+                uint32_t pt = stPT[s.q];
+                s.ps = (int)(pt & 0xFFFFu);
+                s.ts = (int)(pt >> 16);
+            }
+        }
+        else
+            break;
+    }
+    if (s.q < 0)
+    {
+        s.q = 0;
+        s.Hs = H;
+        s.ps = j;
+        s.ts = 0;
+    }
+    else
+    {
+        int w = vc_sep(s.ps, s.Hs, j, H);
+        if (w < ntgt)
+        {
+            stH[s.q] = s.Hs;
+            stPT[s.q] = (uint32_t)s.ps | ((uint32_t)s.ts << 16);
+            ++s.q;
+            s.Hs = H;
+            s.ps = j;
+            s.ts = w;
+        }
+    }
+}
+
 template <class Emit>
 VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt,
                             vc_u64* stH, uint32_t* stPT, Emit emit)
 {
-    int q = -1;
-    vc_u64 Hs = 0;
-    int ps = 0, ts = 0;
-    for (int j = 0; j < ncand; ++j)
+    vc_env_state s;
+    s.q = -1;
+    s.Hs = 0;
+    s.ps = 0;
+    s.ts = 0;
+    vc_u64 bankA[VC_PF], bankB[VC_PF];
+#define VC_FETCH(bank, j0)                                                                         \
+    _Pragma("unroll") for (int k = 0; k < VC_PF; ++k)                                              \
+        bank[k] = ((j0) + k < ncand) ? VC_LOAD_STREAM(in + (long)((j0) + k) * stride) : (vc_u64)VC_INF;
+#define VC_CONSUME(bank, j0)                                                                       \
+    _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) vc_env_push(s, bank[k], (j0) + k, ntgt, stH, stPT);
+    VC_FETCH(bankA, 0)
+    for (int j0 = 0; j0 < ncand; j0 += 2 * VC_PF)
     {
-        vc_u64 H = in[(long)j * stride];
-        if (H == VC_INF)
-            continue;
-        while (q >= 0)
-        {
-            if (vc_eval(Hs, ps, ts) > vc_eval(H, j, ts))
-            { // the top loses already where its interval starts: it wins nowhere
-                --q;
-                if (q >= 0)
-                {
-                    Hs = stH[q];
-                    uint32_t pt = stPT[q];
-                    ps = (int)(pt & 0xFFFFu);
-                    ts = (int)(pt >> 16);
-                }
-            }
-            else
-                break;
-        }
-        if (q < 0)
-        {
-            q = 0;
-            Hs = H;
-            ps = j;
-            ts = 0;
-        }
-        else
-        {
-            int w = vc_sep(ps, Hs, j, H);
-            if (w < ntgt)
-            {
-                stH[q] = Hs;
-                stPT[q] = (uint32_t)ps | ((uint32_t)ts << 16);
-                ++q;
-                Hs = H;
-                ps = j;
-                ts = w;
-            }
-        }
+        VC_FETCH(bankB, j0 + VC_PF)
+        VC_CONSUME(bankA, j0)
+        VC_FETCH(bankA, j0 + 2 * VC_PF)
+        VC_CONSUME(bankB, j0 + VC_PF)
     }
+#undef VC_FETCH
+#undef VC_CONSUME
     // one uniform backward loop (a line without candidates emits VC_INF) so that a warp whose
     // lanes each own a line stays convergent at the emit() call and may synchronise inside it
+    int q = s.q;
+    vc_u64 Hs = s.Hs;
+    int ps = s.ps, ts = s.ts;
     const bool empty = q < 0;
     for (int t = ntgt - 1; t >= 0; --t)
     {

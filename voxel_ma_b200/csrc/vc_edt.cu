@@ -17,6 +17,10 @@
 #include "vc_internal.h"
 
 // ---- pass Z -----------------------------------------------------------------------------------
+// One thread walks one z-line's site list over a chunk of PZ_CHUNK planes (blockIdx.y = chunk), so
+// the grid has (lines x chunks) threads instead of one per line; lanes are adjacent lines (cy
+// fastest), every store is a coalesced 256-byte row of G1.
+#define PZ_CHUNK 32
 __global__ void __launch_bounds__(256)
     k_pass_z(const int* __restrict__ line_ptr, const u64* __restrict__ ent, u64* __restrict__ G1, int nlines, int z0,
              int zc)
@@ -24,18 +28,20 @@ __global__ void __launch_bounds__(256)
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines)
         return;
+    const int zb = z0 + blockIdx.y * PZ_CHUNK;
+    const int ze = min(zb + PZ_CHUNK, zc);
     const int first = line_ptr[l], last = line_ptr[l + 1];
-    u64* out = G1 + l;
     const size_t plane = (size_t)nlines;
+    u64* out = G1 + l + plane * (size_t)(zb - z0);
     if (first == last)
     {
-        for (int vz = z0; vz < zc; ++vz, out += plane)
+        for (int vz = zb; vz < ze; ++vz, out += plane)
             __stcs(out, (u64)VC_INF);
         return;
     }
     int nxt = first; // index of the first entry with cz > vz
     u64 below = VC_INF, above = ent[first];
-    for (int vz = z0; vz < zc; ++vz, out += plane)
+    for (int vz = zb; vz < ze; ++vz, out += plane)
     {
         while (nxt < last && (int)(above >> 32) <= vz)
         {
@@ -152,7 +158,7 @@ int st_closest_lattice(vc_ctx* c)
     VC_CUDA(c, c->id.ensure(nv * 4));
     VC_CUDA(c, c->d2.ensure(nv * 4));
     const int nlines = CX * CY;
-    VC_LAUNCH(c, "edt_pass_z", k_pass_z, vc_blocks((size_t)nlines, 256), 256, 0, c->line_ptr.as<int>(),
+    VC_LAUNCH(c, "edt_pass_z", k_pass_z, dim3(vc_blocks((size_t)nlines, 256), (nplanes + PZ_CHUNK - 1) / PZ_CHUNK), 256, 0, c->line_ptr.as<int>(),
               c->line_ent.as<u64>(), c->g1.as<u64>(), nlines, c->z0, c->zc);
     int m = (CX > CY ? CX : CY) + 1;
     if (m <= 264)

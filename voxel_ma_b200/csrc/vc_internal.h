@@ -62,6 +62,8 @@ struct vc_ctx
          have_measures = false;
     bool lattice = true; // sites lie on the corner lattice -> dense transform
     DevBuf vol, inside;
+    DevBuf bits; // occupancy bit rows: u32[(z - zlo) * ny + y][wr], bit x & 31 of word x >> 5; wr = nx / 32 + 1
+    int wr = 0;
     // site candidates of this slab (unsorted) and the global, numbered site set
     DevBuf cand_key, cand_corner;
     int64_t ncand = 0;

@@ -19,81 +19,161 @@ __device__ __forceinline__ float vc_dist2f(float ax, float ay, float az, float b
 }
 
 // =============================================================================================
-// K5  dense cell measures (dictionary of SURVEY section 0).  One thread per grid vertex v; the 7
-// cells anchored at v need the sites of the 8 vertices of v's cube.  sqrt is monotone and
-// correctly rounded, so max over edges of sqrt(d2) == sqrt(max d2): the 12 edge terms are reduced
-// as squared distances and only the 7 outputs (+ radius) take a square root.
+// K5  dense cell measures (dictionary of SURVEY section 0).  The 7 cells anchored at grid vertex v
+// need the closest sites of the 8 vertices of v's cube.  sqrt is monotone and correctly rounded,
+// so max over edges of sqrt(d2) == sqrt(max d2): the 12 edge terms are reduced as squared
+// distances and only the 7 outputs (+ radius) take a square root.
+//
+// A block owns a 32 x 8 (x,y) tile and marches up a chunk of z planes.  Per plane it fetches the
+// (32+1) x (8+1) ids once (id 4 B + flag 1 B per vertex: the algorithmic read), gathers each id's
+// site from the L2-resident table once, and parks (site, flags) in shared memory; a thread keeps
+// the 4 records of its own column for plane z in registers and reads the 4 of plane z+1 from
+// shared memory, so the 8 x 4 B outputs per vertex are the only HBM traffic that scales.
+// The id / flag loads of plane z+2 are issued before plane z+1 is consumed.
 // id: planes [z0, zc) (zc = z1+1 halo when z1 < nz); inside: planes [zlo, zhi).
 // =============================================================================================
-__global__ void __launch_bounds__(256)
+#define CM_TX 32
+#define CM_TY 8
+#define CM_ENT ((CM_TX + 1) * (CM_TY + 1)) // 297 records per plane
+#define CM_PER ((CM_ENT + CM_TX * CM_TY - 1) / (CM_TX * CM_TY)) // records a thread loads per plane (2)
+
+struct CmRec
+{
+    float x, y, z;
+    u32 f; // bit 0: vertex exists and has a site; bit 1: vertex is inside
+};
+
+__device__ __forceinline__ float cm_e2(const CmRec& a, const CmRec& b)
+{
+    return (a.f & b.f & 1u) ? vc_dist2f(a.x, a.y, a.z, b.x, b.y, b.z) : 0.0f;
+}
+
+__global__ void __launch_bounds__(CM_TX* CM_TY)
     k_cell_measures(const int* __restrict__ id, const u8* __restrict__ inside, const float4* __restrict__ site,
-                    int nx, int ny, int nz, int z0, int z1, int zc, int zlo, float* __restrict__ edge3,
+                    int nx, int ny, int z0, int z1, int zc, int zlo, int zchunk, float* __restrict__ edge3,
                     float* __restrict__ face3, float* __restrict__ cube, float* __restrict__ radius)
 {
-    const size_t nv = (size_t)nx * ny * (size_t)(z1 - z0);
-    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= nv)
-        return;
-    const int x = (int)(o % nx);
-    const size_t r = o / nx;
-    const int y = (int)(r % ny);
-    const int z = z0 + (int)(r / ny);
+    __shared__ float4 tile[2][CM_TY + 1][CM_TX + 1];
+    const int tx = threadIdx.x & (CM_TX - 1), ty = threadIdx.x / CM_TX;
+    const int x0 = blockIdx.x * CM_TX, y0 = blockIdx.y * CM_TY;
+    const int zs = z0 + blockIdx.z * zchunk, ze = min(zs + zchunk, z1);
+    const int x = x0 + tx, y = y0 + ty;
+    const size_t plane = (size_t)nx * ny;
+    const size_t nv = plane * (size_t)(z1 - z0);
 
-    float sx[8], sy[8], sz[8];
-    bool ok[8], in[8];
+    // the records this thread loads each plane: e = threadIdx.x + k*256 -> (hy, hx) of the halo tile
+    size_t lo[CM_PER];
+    int hyx[CM_PER];
+    bool lok[CM_PER];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < CM_PER; ++k)
     {
-        int xx = x + (k & 1), yy = y + ((k >> 1) & 1), zz = z + ((k >> 2) & 1);
-        ok[k] = xx < nx && yy < ny && zz < zc;
-        in[k] = false;
-        sx[k] = sy[k] = sz[k] = 0.0f;
-        if (ok[k])
+        int e = threadIdx.x + k * CM_TX * CM_TY;
+        int hy = e / (CM_TX + 1), hx = e - hy * (CM_TX + 1);
+        lok[k] = e < CM_ENT && x0 + hx < nx && y0 + hy < ny;
+        hyx[k] = e < CM_ENT ? hy * (CM_TX + 1) + hx : -1;
+        lo[k] = (size_t)(x0 + hx) + (size_t)nx * (size_t)(y0 + hy);
+    }
+    int sid[CM_PER];
+    u32 fin[CM_PER];
+    auto fetch_ids = [&](int zz)
+    {
+#pragma unroll
+        for (int k = 0; k < CM_PER; ++k)
         {
-            size_t plane = (size_t)nx * ny;
-            int sid = __ldg(id + (size_t)xx + (size_t)nx * yy + plane * (size_t)(zz - z0));
-            in[k] = __ldg(inside + (size_t)xx + (size_t)nx * yy + plane * (size_t)(zz - zlo)) != 0;
-            if (sid >= 0)
+            sid[k] = -1;
+            fin[k] = 0;
+            if (lok[k] && zz < zc)
             {
-                float4 s = __ldg(site + sid);
-                sx[k] = s.x;
-                sy[k] = s.y;
-                sz[k] = s.z;
+                sid[k] = __ldcs(id + lo[k] + plane * (size_t)(zz - z0));
+                fin[k] = __ldg(inside + lo[k] + plane * (size_t)(zz - zlo)) ? 2u : 0u;
             }
-            else
-                ok[k] = false;
         }
-    }
-#define E2(a, b) ((ok[a] && ok[b]) ? vc_dist2f(sx[a], sy[a], sz[a], sx[b], sy[b], sz[b]) : 0.0f)
-    // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
-    const float x0 = E2(0, 1), x1 = E2(2, 3), x2 = E2(4, 5), x3 = E2(6, 7);
-    const float y0 = E2(0, 2), y1 = E2(1, 3), y2 = E2(4, 6), y3 = E2(5, 7);
-    const float w0 = E2(0, 4), w1 = E2(1, 5), w2 = E2(2, 6), w3 = E2(3, 7);
-#undef E2
-    if (edge3)
+    };
+    auto park = [&](int buf)
     {
-        __stcs(edge3 + o, (in[0] && in[1]) ? __fsqrt_rn(x0) : 0.0f);
-        __stcs(edge3 + nv + o, (in[0] && in[2]) ? __fsqrt_rn(y0) : 0.0f);
-        __stcs(edge3 + 2 * nv + o, (in[0] && in[4]) ? __fsqrt_rn(w0) : 0.0f);
-    }
-    const float fxy = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
-    const float fxz = fmaxf(fmaxf(x0, x2), fmaxf(w0, w1));
-    const float fyz = fmaxf(fmaxf(y0, y2), fmaxf(w0, w2));
-    if (face3)
+#pragma unroll
+        for (int k = 0; k < CM_PER; ++k)
+            if (hyx[k] >= 0)
+            {
+                float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                u32 f = fin[k];
+                if (sid[k] >= 0)
+                {
+                    r = __ldg(site + sid[k]);
+                    f |= 1u;
+                }
+                r.w = __uint_as_float(f);
+                (&tile[buf][0][0])[hyx[k]] = r;
+            }
+    };
+    auto rec = [&](int buf, int dy, int dx) -> CmRec
     {
-        __stcs(face3 + o, (in[0] && in[1] && in[2] && in[3]) ? __fsqrt_rn(fxy) : 0.0f);
-        __stcs(face3 + nv + o, (in[0] && in[1] && in[4] && in[5]) ? __fsqrt_rn(fxz) : 0.0f);
-        __stcs(face3 + 2 * nv + o, (in[0] && in[2] && in[4] && in[6]) ? __fsqrt_rn(fyz) : 0.0f);
-    }
-    if (cube)
+        float4 v = tile[buf][ty + dy][tx + dx];
+        CmRec r;
+        r.x = v.x;
+        r.y = v.y;
+        r.z = v.z;
+        r.f = __float_as_uint(v.w);
+        return r;
+    };
+
+    fetch_ids(zs);
+    park(0);
+    fetch_ids(zs + 1);
+    __syncthreads();
+    CmRec a0 = rec(0, 0, 0), a1 = rec(0, 0, 1), a2 = rec(0, 1, 0), a3 = rec(0, 1, 1);
+    float ex0 = cm_e2(a0, a1), ex1 = cm_e2(a2, a3), ey0 = cm_e2(a0, a2), ey1 = cm_e2(a1, a3);
+    const bool live = x < nx && y < ny;
+    for (int z = zs; z < ze; ++z)
     {
-        float m = fmaxf(fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)), fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-        m = fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)));
-        bool all = in[0] && in[1] && in[2] && in[3] && in[4] && in[5] && in[6] && in[7];
-        __stcs(cube + o, all ? __fsqrt_rn(m) : 0.0f);
+        const int buf = (z - zs + 1) & 1;
+        park(buf);          // plane z+1 (ids fetched one iteration ago)
+        fetch_ids(z + 2);   // in flight while plane z is computed
+        __syncthreads();
+        const CmRec b0 = rec(buf, 0, 0), b1 = rec(buf, 0, 1), b2 = rec(buf, 1, 0), b3 = rec(buf, 1, 1);
+        // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
+        const float ex2 = cm_e2(b0, b1), ex3 = cm_e2(b2, b3), ey2 = cm_e2(b0, b2), ey3 = cm_e2(b1, b3);
+        const float w0 = cm_e2(a0, b0), w1 = cm_e2(a1, b1), w2 = cm_e2(a2, b2), w3 = cm_e2(a3, b3);
+        if (live)
+        {
+            const size_t o = (size_t)x + (size_t)nx * (size_t)y + plane * (size_t)(z - z0);
+            const u32 i0 = a0.f & 2u, i1 = a1.f & 2u, i2 = a2.f & 2u, i3 = a3.f & 2u;
+            const u32 i4 = b0.f & 2u, i5 = b1.f & 2u, i6 = b2.f & 2u, i7 = b3.f & 2u;
+            if (edge3)
+            {
+                __stcs(edge3 + o, (i0 & i1) ? __fsqrt_rn(ex0) : 0.0f);
+                __stcs(edge3 + nv + o, (i0 & i2) ? __fsqrt_rn(ey0) : 0.0f);
+                __stcs(edge3 + 2 * nv + o, (i0 & i4) ? __fsqrt_rn(w0) : 0.0f);
+            }
+            if (face3)
+            {
+                const float fxy = fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1));
+                const float fxz = fmaxf(fmaxf(ex0, ex2), fmaxf(w0, w1));
+                const float fyz = fmaxf(fmaxf(ey0, ey2), fmaxf(w0, w2));
+                __stcs(face3 + o, (i0 & i1 & i2 & i3) ? __fsqrt_rn(fxy) : 0.0f);
+                __stcs(face3 + nv + o, (i0 & i1 & i4 & i5) ? __fsqrt_rn(fxz) : 0.0f);
+                __stcs(face3 + 2 * nv + o, (i0 & i2 & i4 & i6) ? __fsqrt_rn(fyz) : 0.0f);
+            }
+            if (cube)
+            {
+                float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
+                m = fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)));
+                __stcs(cube + o, (i0 & i1 & i2 & i3 & i4 & i5 & i6 & i7) ? __fsqrt_rn(m) : 0.0f);
+            }
+            if (radius)
+                __stcs(radius + o,
+                       (a0.f & 1u) ? __fsqrt_rn(vc_dist2f(a0.x, a0.y, a0.z, (float)x, (float)y, (float)z)) : 0.0f);
+        }
+        a0 = b0;
+        a1 = b1;
+        a2 = b2;
+        a3 = b3;
+        ex0 = ex2;
+        ex1 = ex3;
+        ey0 = ey2;
+        ey1 = ey3;
     }
-    if (radius)
-        __stcs(radius + o, ok[0] ? __fsqrt_rn(vc_dist2f(sx[0], sy[0], sz[0], (float)x, (float)y, (float)z)) : 0.0f);
 }
 
 int st_measures(vc_ctx* c, bool want_radius)
@@ -108,8 +188,18 @@ int st_measures(vc_ctx* c, bool want_radius)
     VC_CUDA(c, c->cube.ensure(nv * 4));
     if (want_radius)
         VC_CUDA(c, c->radius.ensure(nv * 4));
-    VC_LAUNCH(c, "cell_measures", k_cell_measures, vc_blocks(nv, 256), 256, 0, c->id.as<int>(), c->inside.as<u8>(),
-              c->site_xyz.as<float4>(), c->nx, c->ny, c->nz, c->z0, c->z1, c->zc, c->zlo, c->edge3.as<float>(),
+    // z chunks: long enough to amortise the one extra plane a chunk loads, short enough that the grid
+    // is several waves of the SMs
+    const int nplanes = c->z1 - c->z0;
+    const unsigned gx = (c->nx + CM_TX - 1) / CM_TX, gy = (c->ny + CM_TY - 1) / CM_TY;
+    int zchunk = 32;
+    while (zchunk > 4 && (size_t)gx * gy * ((nplanes + zchunk - 1) / zchunk) < (size_t)c->sm_count * 16)
+        zchunk >>= 1;
+    dim3 grid(gx, gy, (nplanes + zchunk - 1) / zchunk);
+    if (grid.y > 65535u || grid.z > 65535u)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "grid too large for the measures kernel");
+    VC_LAUNCH(c, "cell_measures", k_cell_measures, grid, CM_TX * CM_TY, 0, c->id.as<int>(), c->inside.as<u8>(),
+              c->site_xyz.as<float4>(), c->nx, c->ny, c->z0, c->z1, c->zc, c->zlo, zchunk, c->edge3.as<float>(),
               c->face3.as<float>(), c->cube.as<float>(), want_radius ? c->radius.as<float>() : nullptr);
     VC_CUDA(c, cudaGetLastError());
     c->have_measures = true;

@@ -8,12 +8,17 @@
 
 // =============================================================================================
 // K1  classify: inside <=> value > 0.0  (NaN, 0, -0 are outside).  5 B / voxel: one 128-bit load,
-// one 32-bit store per 4 voxels.
+// one 32-bit store per 4 voxels.  When rows are whole 32-voxel words (nx % 32 == 0) the same pass
+// also packs the flags into the occupancy bit rows the site detection works on: each thread's 4
+// flags are a nibble, 8 neighbouring lanes are OR-combined with three shuffles into one word.
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_classify_f32(const float* __restrict__ vol, u8* __restrict__ inside, size_t n)
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+    k_classify_f32(const float* __restrict__ vol, u8* __restrict__ inside, u32* __restrict__ bits, size_t n, int words_per_row,
+                   int wr)
 {
     size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
     for (; i4 + 3 < n; i4 += stride)
     {
         float4 v = __ldcs(reinterpret_cast<const float4*>(vol + i4));
@@ -23,11 +28,64 @@ __global__ void __launch_bounds__(256) k_classify_f32(const float* __restrict__ 
         o.z = v.z > 0.0f;
         o.w = v.w > 0.0f;
         *reinterpret_cast<uchar4*>(inside + i4) = o;
+        if (PACK)
+        {
+            const int lane = threadIdx.x & 31;
+            u32 w = ((u32)o.x | ((u32)o.y << 1) | ((u32)o.z << 2) | ((u32)o.w << 3)) << (4 * (lane & 7));
+            const u32 grp = 0xFFu << (lane & 24); // the 8 lanes of one word leave the loop together
+            w |= __shfl_xor_sync(grp, w, 1);
+            w |= __shfl_xor_sync(grp, w, 2);
+            w |= __shfl_xor_sync(grp, w, 4);
+            if ((lane & 7) == 0)
+            {
+                size_t wflat = i4 >> 5;
+                size_t row = wflat / (size_t)words_per_row;
+                bits[row * (size_t)wr + (wflat - row * (size_t)words_per_row)] = w;
+            }
+        }
     }
     // tail (n not a multiple of 4): the thread that would own the last partial vector
-    if (i4 < n && i4 + 3 >= n)
+    if (!PACK && i4 < n && i4 + 3 >= n)
         for (size_t i = i4; i < n; ++i)
             inside[i] = vol[i] > 0.0f;
+}
+
+// Occupancy bit rows from the byte flags, any nx: one thread per word (row, w).
+__global__ void __launch_bounds__(256) k_pack_bits(const u8* __restrict__ inside, u32* __restrict__ bits, size_t nrows, int nx, int wr)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * (size_t)wr)
+        return;
+    size_t row = i / (size_t)wr;
+    int w = (int)(i - row * (size_t)wr);
+    int cnt = nx - 32 * w;
+    cnt = cnt > 32 ? 32 : cnt;
+    const u8* src = inside + row * (size_t)nx + 32 * (size_t)w;
+    u32 word = 0;
+    if ((nx & 3) == 0)
+    { // rows are 4-byte aligned and cnt is a multiple of 4
+        for (int k = 0; 4 * k < cnt; ++k)
+        {
+            u32 v = __ldg(reinterpret_cast<const u32*>(src) + k);
+            u32 nib = (v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u);
+            word |= nib << (4 * k);
+        }
+    }
+    else
+        for (int b = 0; b < cnt; ++b)
+            word |= (__ldg(src + b) ? 1u : 0u) << b;
+    bits[i] = word;
+}
+
+// flags -> bit rows for the resident planes (used when classification did not pack them itself)
+static int pack_bits(vc_ctx* c)
+{
+    const size_t nrows = (size_t)c->ny * (size_t)(c->zhi - c->zlo);
+    c->wr = c->nx / 32 + 1;
+    VC_CUDA(c, c->bits.ensure(nrows * (size_t)c->wr * 4 + 16));
+    VC_LAUNCH(c, "pack_bits", k_pack_bits, vc_blocks(nrows * (size_t)c->wr, 256), 256, 0, c->inside.as<u8>(), c->bits.as<u32>(),
+              nrows, c->nx, c->wr);
+    return VC_OK;
 }
 
 // Tao's in-memory order double[x][y][z] (z fastest) -> flags [z][y][x]; 32x32 (x,z) tile per y.
@@ -55,11 +113,25 @@ int st_classify(vc_ctx* c)
 {
     if (!c->have_vol)
         return vc_fail(c, VC_ERR_STATE, "vc_classify_grid: no volume uploaded");
-    size_t n = (size_t)c->nx * c->ny * (size_t)(c->zhi - c->zlo);
+    const size_t nrows = (size_t)c->ny * (size_t)(c->zhi - c->zlo);
+    size_t n = (size_t)c->nx * nrows;
     VC_CUDA(c, c->inside.ensure(n + 16));
     size_t want = (n / 4 + 255) / 256 + 1, cap = (size_t)c->sm_count * 16;
     unsigned blocks = (unsigned)(want < cap ? want : cap);
-    VC_LAUNCH(c, "classify_f32", k_classify_f32, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(), n);
+    if ((c->nx & 31) == 0)
+    {
+        c->wr = c->nx / 32 + 1;
+        VC_CUDA(c, c->bits.ensure(nrows * (size_t)c->wr * 4 + 16));
+        VC_CUDA(c, cudaMemsetAsync(c->bits.p, 0, nrows * (size_t)c->wr * 4, c->stream)); // the pad word of every row
+        VC_LAUNCH(c, "classify_f32", k_classify_f32<true>, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(),
+                  c->bits.as<u32>(), n, c->nx / 32, c->wr);
+    }
+    else
+    {
+        VC_LAUNCH(c, "classify_f32", k_classify_f32<false>, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(),
+                  (u32*)nullptr, n, 0, 0);
+        VC_TRY(pack_bits(c));
+    }
     VC_CUDA(c, cudaGetLastError());
     c->have_inside = true;
     c->have_sites = c->have_closest = c->have_measures = false;
@@ -86,10 +158,13 @@ int st_upload_f64_zfast(vc_ctx* c, const double* vol)
     dim3 grid((c->nx + 31) / 32, (c->nz + 31) / 32, c->ny), block(32, 8);
     VC_LAUNCH(c, "classify_f64_zfast", k_classify_f64_zfast, grid, block, 0, tmp.as<double>(), c->inside.as<u8>(),
               c->nx, c->ny, c->nz);
+    int ps = pack_bits(c);
     e = cudaStreamSynchronize(c->stream);
     tmp.release();
     if (e != cudaSuccess)
         return vc_fail(c, VC_ERR_CUDA, "classify f64", e);
+    if (ps != VC_OK)
+        return ps;
     c->have_vol = false; // only the flags are kept for a double volume
     c->have_inside = true;
     c->have_sites = c->have_closest = c->have_measures = false;
@@ -97,56 +172,93 @@ int st_upload_f64_zfast(vc_ctx* c, const double* vol)
 }
 
 // =============================================================================================
-// K2  site detection: one thread per corner of the slab's corner planes [czb,cze).  A corner is a
-// site iff its 8 incident voxels (out of bounds = 0) are not all equal; its first-encounter key
-// comes from vc_site_key.  Warp-aggregated append; the order of the appended records does not
-// matter because the keys are unique and sorted afterwards.
+// K2  site detection on the occupancy bit rows.  A corner (cx,cy,cz) is a site iff its 8 incident
+// voxels (out of bounds = 0) are neither all 0 nor all 1.  One thread owns the 32 corners
+// cx = 32w .. 32w+31 of corner row (cy,cz): with A = OR and B = AND of the four voxel rows
+// (y in {cy-1,cy}, z in {cz-1,cz}; a row out of bounds reads 0), and the same words shifted by one
+// voxel for x-1,
+//     site word = (A | A') & ~(B & B')
+// so the count pass is a handful of word operations per 32 corners.  The emit pass expands the set
+// bits only: occupancy / in-bounds bytes of the 8 voxels -> first-encounter key (vc_site_key).
+// Warp-aggregated append; the order of the appended records does not matter because the keys are
+// unique and sorted afterwards.
 // =============================================================================================
 template <bool EMIT>
 __global__ void __launch_bounds__(256)
-    k_detect_sites(const u8* __restrict__ inside, int nx, int ny, int nz, int zlo, int czb, int cze,
+    k_detect_sites(const u32* __restrict__ bits, int wr, int nx, int ny, int nz, int zlo, int czb, int cze,
                    u64* __restrict__ keys, u64* __restrict__ corners, u64* __restrict__ counter)
 {
-    const int CX = nx + 1, CY = ny + 1;
-    size_t total = (size_t)CX * CY * (size_t)(cze - czb);
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 key = VC_INF;
-    int cx = 0, cy = 0, cz = 0;
+    const int CY = ny + 1;
+    const size_t total = (size_t)wr * CY * (size_t)(cze - czb);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 site = 0, cur[4] = {0, 0, 0, 0}, prv[4] = {0, 0, 0, 0};
+    int w = 0, cy = 0, cz = 0;
+    u32 rows_in = 0; // bit (b*2+c): voxel row (cy-1+b, cz-1+c) is inside the volume
     if (i < total)
     {
-        cx = (int)(i % CX);
-        size_t r = i / CX;
+        w = (int)(i % wr);
+        size_t r = i / wr;
         cy = (int)(r % CY);
         cz = czb + (int)(r / CY);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            int y = cy - 1 + (k >> 1), z = cz - 1 + (k & 1);
+            if (y >= 0 && y < ny && z >= 0 && z < nz)
+            {
+                rows_in |= 1u << k;
+                const u32* row = bits + ((size_t)(z - zlo) * ny + y) * (size_t)wr;
+                cur[k] = __ldg(row + w);
+                prv[k] = w > 0 ? __ldg(row + w - 1) : 0u;
+            }
+        }
+        const u32 A = cur[0] | cur[1] | cur[2] | cur[3], Ap = prv[0] | prv[1] | prv[2] | prv[3];
+        const u32 B = cur[0] & cur[1] & cur[2] & cur[3], Bp = prv[0] & prv[1] & prv[2] & prv[3];
+        const u32 any8 = A | (A << 1) | (Ap >> 31);
+        const u32 all8 = B & ((B << 1) | (Bp >> 31));
+        const int ncorner = nx + 1 - 32 * w; // corners of this word that exist (cx <= nx)
+        const u32 cmask = ncorner >= 32 ? 0xFFFFFFFFu : (ncorner <= 0 ? 0u : ((1u << ncorner) - 1u));
+        site = any8 & ~all8 & cmask;
+    }
+    const int cnt = __popc(site);
+    // warp-aggregated reservation: exclusive prefix of cnt over the lanes, one atomic per warp
+    const int lane = threadIdx.x & 31;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (warp_total == 0)
+        return;
+    u64 base = 0;
+    if (lane == 31)
+        base = atomicAdd(counter, (u64)warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!EMIT)
+        return;
+    u64 pos = base + (u64)(incl - cnt);
+    while (site)
+    {
+        const int b = __ffs(site) - 1;
+        site &= site - 1;
+        const int cx = 32 * w + b;
         u32 occ = 0, inb = 0;
 #pragma unroll
-        for (int bit = 0; bit < 8; ++bit)
-        {
-            int x = cx - 1 + (bit >> 2), y = cy - 1 + ((bit >> 1) & 1), z = cz - 1 + (bit & 1);
-            bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
-            u32 o = 0;
-            if (in)
-                o = __ldg(inside + (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)(z - zlo))) ? 1u : 0u;
-            occ |= o << bit;
-            inb |= (in ? 1u : 0u) << bit;
+        for (int k = 0; k < 4; ++k)
+        { // voxel (cx-1+a, cy-1+(k>>1), cz-1+(k&1)) -> bit a*4 + k of occ / inb
+            const u32 lo = b > 0 ? (cur[k] >> (b - 1)) & 1u : prv[k] >> 31; // x = cx-1
+            const u32 hi = (cur[k] >> b) & 1u;                              // x = cx
+            occ |= (lo << k) | (hi << (4 + k));
+            const u32 rin = (rows_in >> k) & 1u;
+            inb |= ((cx >= 1 ? rin : 0u) << k) | ((cx < nx ? rin : 0u) << (4 + k));
         }
-        key = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
-    }
-    bool is = key != VC_INF;
-    unsigned m = __ballot_sync(0xffffffffu, is);
-    if (m == 0)
-        return;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(m) - 1;
-    u64 base = 0;
-    if (lane == leader)
-        base = atomicAdd(counter, (u64)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (EMIT && is)
-    {
-        u64 pos = base + __popc(m & ((1u << lane) - 1));
-        keys[pos] = key;
+        keys[pos] = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
         corners[pos] = vc_pack_corner(cx, cy, cz);
+        ++pos;
     }
 }
 
@@ -158,12 +270,12 @@ int st_detect_sites(vc_ctx* c)
     int czb = c->z0, cze = (c->z1 == c->nz) ? c->nz + 1 : c->z1;
     if (c->zlo > (czb > 0 ? czb - 1 : 0) || c->zhi < (cze - 1 < c->nz ? cze : c->nz))
         return vc_fail(c, VC_ERR_STATE, "resident voxel planes do not cover the slab's corner planes");
-    size_t total = (size_t)(c->nx + 1) * (c->ny + 1) * (size_t)(cze - czb);
+    size_t total = (size_t)c->wr * (c->ny + 1) * (size_t)(cze - czb);
     VC_CUDA(c, c->scratch.ensure(256));
     u64* counter = c->scratch.as<u64>();
     VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
     unsigned blocks = vc_blocks(total, 256);
-    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<false>, blocks, 256, 0, c->inside.as<u8>(), c->nx, c->ny, c->nz,
+    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<false>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny, c->nz,
               c->zlo, czb, cze, nullptr, nullptr, counter);
     u64 n = 0;
     VC_CUDA(c, cudaMemcpyAsync(&n, counter, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -174,7 +286,7 @@ int st_detect_sites(vc_ctx* c)
     if (n)
     {
         VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
-        VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<true>, blocks, 256, 0, c->inside.as<u8>(), c->nx, c->ny,
+        VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<true>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
                   c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter);
         VC_CUDA(c, cudaGetLastError());
     }
