@@ -74,15 +74,16 @@ VC_HD int vc_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk)
 }
 
 // One line of the separable transform: lower envelope of the candidates in[j*stride], j in
-// [0,ncand), evaluated at targets t in [0,ntgt).  Forward scan keeps the envelope as a stack whose
-// top lives in registers (Hs,ps,ts = word, position, first target it wins); the part below the
-// top lives in stH/stPT (thread-local memory on the device).  The backward scan emits targets
-// ntgt-1 .. 0 through `emit(t, value)`.
+// [0,ncand), evaluated at targets t in [0,ntgt).  The forward scan keeps the envelope as a stack of
+// (word, position, first target it wins); its two upper entries live in registers (top, sec), the
+// rest in stH/stPT (thread-local memory on the device), so a pop is a register move plus a load
+// whose result is not needed before the NEXT pop -- the dependent chain never waits on memory.
+// The backward scan emits targets ntgt-1 .. 0 through `emit(t, value)`.
 //
 // The candidates are fetched VC_PF at a time into two register banks that alternate: while one
 // bank is consumed the loads of the next are already in flight, so a thread keeps up to 2*VC_PF
-// independent 8-byte loads outstanding instead of one (the scan itself is a dependent chain).
-#define VC_PF 8
+// independent 8-byte loads outstanding instead of one.
+#define VC_PF 4
 
 #if defined(__CUDA_ARCH__)
 #define VC_LOAD_STREAM(p) __ldcs(p) // read once: evict-first
@@ -92,51 +93,54 @@ VC_HD int vc_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk)
 
 struct vc_env_state
 {
-    int q;
-    vc_u64 Hs;
+    int q;        // index of the top entry; -1 = empty.  entry q = top, q-1 = sec, 0..q-2 in memory
+    vc_u64 Hs;    // top
     int ps, ts;
+    vc_u64 H2;    // second
+    int p2, t2;
 };
+
+VC_HD void vc_env_pop(vc_env_state& s, const vc_u64* stH, const uint32_t* stPT)
+{
+    --s.q;
+    s.Hs = s.H2;
+    s.ps = s.p2;
+    s.ts = s.t2;
+    if (s.q >= 1)
+    {
+        s.H2 = stH[s.q - 1];
+        uint32_t pt = stPT[s.q - 1];
+        s.p2 = (int)(pt & 0xFFFFu);
+        s.t2 = (int)(pt >> 16);
+    }
+}
 
 VC_HD void vc_env_push(vc_env_state& s, vc_u64 H, int j, int ntgt, vc_u64* stH, uint32_t* stPT)
 {
     if (H == VC_INF)
         return;
-    while (s.q >= 0)
+    // the top loses already where its interval starts: it wins nowhere
+    while (s.q >= 0 && vc_eval(s.Hs, s.ps, s.ts) > vc_eval(H, j, s.ts))
+        vc_env_pop(s, stH, stPT);
+    int w = 0;
+    if (s.q >= 0)
     {
-        if (vc_eval(s.Hs, s.ps, s.ts) > vc_eval(H, j, s.ts))
-        { // the top loses already where its interval starts: it wins nowhere
-            --s.q;
-            if (s.q >= 0)
-            {
-                s.Hs = stH[s.q];
-                uint32_t pt = stPT[s.q];
-                s.ps = (int)(pt & 0xFFFFu);
-                s.ts = (int)(pt >> 16);
-            }
-        }
-        else
-            break;
-    }
-    if (s.q < 0)
-    {
-        s.q = 0;
-        s.Hs = H;
-        s.ps = j;
-        s.ts = 0;
-    }
-    else
-    {
-        int w = vc_sep(s.ps, s.Hs, j, H);
-        if (w < ntgt)
+        w = vc_sep(s.ps, s.Hs, j, H);
+        if (w >= ntgt)
+            return; // wins only beyond the last target
+        if (s.q >= 1)
         {
-            stH[s.q] = s.Hs;
-            stPT[s.q] = (uint32_t)s.ps | ((uint32_t)s.ts << 16);
-            ++s.q;
-            s.Hs = H;
-            s.ps = j;
-            s.ts = w;
+            stH[s.q - 1] = s.H2;
+            stPT[s.q - 1] = (uint32_t)s.p2 | ((uint32_t)s.t2 << 16);
         }
+        s.H2 = s.Hs;
+        s.p2 = s.ps;
+        s.t2 = s.ts;
     }
+    ++s.q;
+    s.Hs = H;
+    s.ps = j;
+    s.ts = w;
 }
 
 template <class Emit>
@@ -145,9 +149,8 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
 {
     vc_env_state s;
     s.q = -1;
-    s.Hs = 0;
-    s.ps = 0;
-    s.ts = 0;
+    s.Hs = s.H2 = 0;
+    s.ps = s.ts = s.p2 = s.t2 = 0;
     vc_u64 bankA[VC_PF], bankB[VC_PF];
 #define VC_FETCH(bank, j0)                                                                         \
     _Pragma("unroll") for (int k = 0; k < VC_PF; ++k)                                              \
@@ -166,21 +169,12 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
 #undef VC_CONSUME
     // one uniform backward loop (a line without candidates emits VC_INF) so that a warp whose
     // lanes each own a line stays convergent at the emit() call and may synchronise inside it
-    int q = s.q;
-    vc_u64 Hs = s.Hs;
-    int ps = s.ps, ts = s.ts;
-    const bool empty = q < 0;
+    const bool empty = s.q < 0;
     for (int t = ntgt - 1; t >= 0; --t)
     {
-        emit(t, empty ? (vc_u64)VC_INF : vc_eval(Hs, ps, t));
-        if (t == ts && q > 0)
-        {
-            --q;
-            Hs = stH[q];
-            uint32_t pt = stPT[q];
-            ps = (int)(pt & 0xFFFFu);
-            ts = (int)(pt >> 16);
-        }
+        emit(t, empty ? (vc_u64)VC_INF : vc_eval(s.Hs, s.ps, t));
+        if (t == s.ts && s.q > 0)
+            vc_env_pop(s, stH, stPT);
     }
 }
 

@@ -67,18 +67,21 @@ __global__ void __launch_bounds__(256)
 
 // ---- passes X and Y ------------------------------------------------------------------------------
 // TRANSPOSE = true  (pass X): line g = (vz, cy); input G1 + vz*CX*CY + cy, stride CY; the outputs of
-//   32 lines x 32 targets are staged in shared memory and written as 32 rows of 256 bytes of
-//   G2[g][vx].
+//   32 lines x XY_TW targets are staged in shared memory and written as rows of XY_TW*8 = 128 bytes
+//   of G2[g][vx].
 // TRANSPOSE = false (pass Y): line g = (vz, vx); input G2 + vz*CY*nx + vx, stride nx; outputs go
 //   straight to id/d2x4[(vz*ny + vy)*nx + vx], coalesced across the warp.
-#define XY_THREADS_T 128 // pass X: 4 warps x 8.25 KB of transpose tile = 33 KB static shared memory
+// Both are capped at 64 registers so that 32 warps are resident per SM: each thread keeps
+// 2*VC_PF candidate loads in flight (vc_core.h), which covers the HBM latency-bandwidth product.
+#define XY_THREADS_T 128 // pass X: 4 warps x 4.25 KB of transpose tile
 #define XY_THREADS_D 256 // pass Y
+#define XY_TW 16         // targets per transposed store burst
 template <int MAXC, bool TRANSPOSE>
-__global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D)
+__global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANSPOSE ? 8 : 4)
     k_pass_xy(const u64* __restrict__ in, u64* __restrict__ G2, int* __restrict__ id_out, u32* __restrict__ d2_out,
               long nlines_total, int lines_per_plane, long in_plane_stride, long in_stride, int ncand, int ntgt)
 {
-    __shared__ u64 tile[TRANSPOSE ? XY_THREADS_T / 32 : 1][TRANSPOSE ? 32 : 1][TRANSPOSE ? 33 : 1];
+    __shared__ u64 tile[TRANSPOSE ? XY_THREADS_T / 32 : 1][TRANSPOSE ? 32 : 1][TRANSPOSE ? XY_TW + 1 : 1];
     u64 stH[MAXC];
     u32 stPT[MAXC];
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,37 +94,39 @@ __global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D)
 
     if (TRANSPOSE)
     {
+        const int rsub = lane / XY_TW, col = lane % XY_TW; // a store instruction covers 32/XY_TW rows
         vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stH, stPT,
                          [&](int t, u64 v)
                          {
-                             tile[warp][lane][t & 31] = v;
-                             if ((t & 31) == 0)
+                             tile[warp][lane][t % XY_TW] = v;
+                             if ((t % XY_TW) == 0)
                              {
                                  __syncwarp();
-                                 const int width = min(32, ntgt - t);
+                                 const bool colok = t + col < ntgt;
+                                 u64* dst = G2 + (gwarp + rsub) * (long)ntgt + t + col;
 #pragma unroll 4
-                                 for (int r = 0; r < 32; ++r)
-                                 {
-                                     long gr = gwarp + r;
-                                     if (gr < nlines_total && lane < width)
-                                         G2[gr * (long)ntgt + t + lane] = tile[warp][r][lane];
-                                 }
+                                 for (int r = rsub; r < 32; r += 32 / XY_TW, dst += (long)(32 / XY_TW) * ntgt)
+                                     if (colok && gwarp + r < nlines_total)
+                                         *dst = tile[warp][r][col];
                                  __syncwarp();
                              }
                          });
     }
     else
     {
-        const long obase = plane * (long)ntgt * lines_per_plane + within;
+        const long last = plane * (long)ntgt * lines_per_plane + within + (long)(ntgt - 1) * lines_per_plane;
+        int* pid = id_out + last;
+        u32* pd2 = d2_out + last;
         vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stH, stPT,
                          [&](int t, u64 v)
-                         {
+                         { // targets arrive as ntgt-1 .. 0
                              if (valid)
                              {
-                                 long o = obase + (long)t * lines_per_plane;
-                                 __stcs(id_out + o, (int)(u32)v);
-                                 __stcs(d2_out + o, (u32)(v >> 32));
+                                 __stcs(pid, (int)(u32)v);
+                                 __stcs(pd2, (u32)(v >> 32));
                              }
+                             pid -= lines_per_plane;
+                             pd2 -= lines_per_plane;
                          });
     }
 }

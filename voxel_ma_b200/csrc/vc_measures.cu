@@ -48,7 +48,7 @@ __device__ __forceinline__ float cm_e2(const CmRec& a, const CmRec& b)
     return (a.f & b.f & 1u) ? vc_dist2f(a.x, a.y, a.z, b.x, b.y, b.z) : 0.0f;
 }
 
-__global__ void __launch_bounds__(CM_TX* CM_TY)
+__global__ void __launch_bounds__(CM_TX* CM_TY, 4)
     k_cell_measures(const int* __restrict__ id, const u8* __restrict__ inside, const float4* __restrict__ site,
                     int nx, int ny, int z0, int z1, int zc, int zlo, int zchunk, float* __restrict__ edge3,
                     float* __restrict__ face3, float* __restrict__ cube, float* __restrict__ radius)
@@ -123,9 +123,21 @@ __global__ void __launch_bounds__(CM_TX* CM_TY)
     fetch_ids(zs + 1);
     __syncthreads();
     CmRec a0 = rec(0, 0, 0), a1 = rec(0, 0, 1), a2 = rec(0, 1, 0), a3 = rec(0, 1, 1);
-    float ex0 = cm_e2(a0, a1), ex1 = cm_e2(a2, a3), ey0 = cm_e2(a0, a2), ey1 = cm_e2(a1, a3);
+    // Every one of the 7 cells anchored at v contains v, so a vertex outside the solid reports 0 for
+    // all of them and none of its edge terms is ever used: the distance arithmetic runs only for
+    // inside anchors (in-plane edges of plane z+1 are computed when that plane's anchor is inside,
+    // and carried over to the next iteration).
+    float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;
+    if (a0.f & 2u)
+    {
+        ex0 = cm_e2(a0, a1);
+        ex1 = cm_e2(a2, a3);
+        ey0 = cm_e2(a0, a2);
+        ey1 = cm_e2(a1, a3);
+    }
     const bool live = x < nx && y < ny;
-    for (int z = zs; z < ze; ++z)
+    size_t o = (size_t)x + (size_t)nx * (size_t)y + plane * (size_t)(zs - z0);
+    for (int z = zs; z < ze; ++z, o += plane)
     {
         const int buf = (z - zs + 1) & 1;
         park(buf);          // plane z+1 (ids fetched one iteration ago)
@@ -133,34 +145,54 @@ __global__ void __launch_bounds__(CM_TX* CM_TY)
         __syncthreads();
         const CmRec b0 = rec(buf, 0, 0), b1 = rec(buf, 0, 1), b2 = rec(buf, 1, 0), b3 = rec(buf, 1, 1);
         // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
-        const float ex2 = cm_e2(b0, b1), ex3 = cm_e2(b2, b3), ey2 = cm_e2(b0, b2), ey3 = cm_e2(b1, b3);
-        const float w0 = cm_e2(a0, b0), w1 = cm_e2(a1, b1), w2 = cm_e2(a2, b2), w3 = cm_e2(a3, b3);
+        float ex2 = 0.0f, ex3 = 0.0f, ey2 = 0.0f, ey3 = 0.0f;
+        if ((a0.f | b0.f) & 2u)
+        {
+            ex2 = cm_e2(b0, b1);
+            ex3 = cm_e2(b2, b3);
+            ey2 = cm_e2(b0, b2);
+            ey3 = cm_e2(b1, b3);
+        }
+        float le0 = 0.0f, le1 = 0.0f, le2 = 0.0f, lf0 = 0.0f, lf1 = 0.0f, lf2 = 0.0f, lc = 0.0f;
+        if (a0.f & 2u)
+        {
+            const float w0 = cm_e2(a0, b0), w1 = cm_e2(a1, b1), w2 = cm_e2(a2, b2), w3 = cm_e2(a3, b3);
+            const u32 i1 = a1.f & 2u, i2 = a2.f & 2u, i3 = a3.f & 2u;
+            const u32 i4 = b0.f & 2u, i5 = b1.f & 2u, i6 = b2.f & 2u, i7 = b3.f & 2u;
+            if (i1)
+                le0 = __fsqrt_rn(ex0);
+            if (i2)
+                le1 = __fsqrt_rn(ey0);
+            if (i4)
+                le2 = __fsqrt_rn(w0);
+            if (i1 & i2 & i3)
+                lf0 = __fsqrt_rn(fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1)));
+            if (i1 & i4 & i5)
+                lf1 = __fsqrt_rn(fmaxf(fmaxf(ex0, ex2), fmaxf(w0, w1)));
+            if (i2 & i4 & i6)
+                lf2 = __fsqrt_rn(fmaxf(fmaxf(ey0, ey2), fmaxf(w0, w2)));
+            if (i1 & i2 & i3 & i4 & i5 & i6 & i7)
+            {
+                float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
+                lc = __fsqrt_rn(fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3))));
+            }
+        }
         if (live)
         {
-            const size_t o = (size_t)x + (size_t)nx * (size_t)y + plane * (size_t)(z - z0);
-            const u32 i0 = a0.f & 2u, i1 = a1.f & 2u, i2 = a2.f & 2u, i3 = a3.f & 2u;
-            const u32 i4 = b0.f & 2u, i5 = b1.f & 2u, i6 = b2.f & 2u, i7 = b3.f & 2u;
             if (edge3)
             {
-                __stcs(edge3 + o, (i0 & i1) ? __fsqrt_rn(ex0) : 0.0f);
-                __stcs(edge3 + nv + o, (i0 & i2) ? __fsqrt_rn(ey0) : 0.0f);
-                __stcs(edge3 + 2 * nv + o, (i0 & i4) ? __fsqrt_rn(w0) : 0.0f);
+                __stcs(edge3 + o, le0);
+                __stcs(edge3 + nv + o, le1);
+                __stcs(edge3 + 2 * nv + o, le2);
             }
             if (face3)
             {
-                const float fxy = fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1));
-                const float fxz = fmaxf(fmaxf(ex0, ex2), fmaxf(w0, w1));
-                const float fyz = fmaxf(fmaxf(ey0, ey2), fmaxf(w0, w2));
-                __stcs(face3 + o, (i0 & i1 & i2 & i3) ? __fsqrt_rn(fxy) : 0.0f);
-                __stcs(face3 + nv + o, (i0 & i1 & i4 & i5) ? __fsqrt_rn(fxz) : 0.0f);
-                __stcs(face3 + 2 * nv + o, (i0 & i2 & i4 & i6) ? __fsqrt_rn(fyz) : 0.0f);
+                __stcs(face3 + o, lf0);
+                __stcs(face3 + nv + o, lf1);
+                __stcs(face3 + 2 * nv + o, lf2);
             }
             if (cube)
-            {
-                float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
-                m = fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)));
-                __stcs(cube + o, (i0 & i1 & i2 & i3 & i4 & i5 & i6 & i7) ? __fsqrt_rn(m) : 0.0f);
-            }
+                __stcs(cube + o, lc);
             if (radius)
                 __stcs(radius + o,
                        (a0.f & 1u) ? __fsqrt_rn(vc_dist2f(a0.x, a0.y, a0.z, (float)x, (float)y, (float)z)) : 0.0f);
