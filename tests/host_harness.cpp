@@ -1,5 +1,5 @@
 // tests/host_harness.cpp -- TEST ONLY.  Drives the exact-arithmetic core the CUDA kernels are built
-// from (voxel_ma_b200/csrc/vc_core.h: vc_site_key, vc_nearest_on_zline, vc_envelope_line, vc_sep)
+// from (voxel_ma_b200/csrc/vc_core.h: vc_site_key, vc_nearest_on_zline, vc_envelope_line)
 // line by line on the CPU, so the algorithm can be checked against the oracle in the `not gpu`
 // suite.  Nothing here is reachable from the product library.
 #include <algorithm>
@@ -84,18 +84,18 @@ extern "C"
                 }
             }
         int maxc = std::max(CX, CY) + 1;
-        std::vector<vc_u64> stH(maxc);
-        std::vector<uint32_t> stPT(maxc);
+        std::vector<vc_u64> stkv(maxc);
+        vc_stack_array stk{stkv.data()};
         for (int vz = 0; vz < nzs; ++vz)
             for (int cy = 0; cy < CY; ++cy)
             {
                 vc_u64* row = &G2[((size_t)vz * CY + cy) * nx];
-                vc_envelope_line(&G1[(size_t)vz * CX * CY + cy], (long)CY, CX, nx, stH.data(), stPT.data(),
+                vc_envelope_line(&G1[(size_t)vz * CX * CY + cy], (long)CY, CX, nx, stk,
                                  [&](int t, vc_u64 v) { row[t] = v; });
             }
         for (int vz = 0; vz < nzs; ++vz)
             for (int vx = 0; vx < nx; ++vx)
-                vc_envelope_line(&G2[(size_t)vz * CY * nx + vx], (long)nx, CY, ny, stH.data(), stPT.data(),
+                vc_envelope_line(&G2[(size_t)vz * CY * nx + vx], (long)nx, CY, ny, stk,
                                  [&](int t, vc_u64 v)
                                  {
                                      size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
@@ -104,15 +104,13 @@ extern "C"
                                  });
     }
 
-    int hh_floor_div(int a, int b) { return vc_floor_div(a, b); }
-    int hh_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk) { return vc_sep(pi, Hi, pk, Hk); }
 
     // one line of the transform on caller data (robustness tests with 2048-scale coordinates)
     void hh_envelope(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
     {
-        std::vector<vc_u64> stH(ncand + 1);
-        std::vector<uint32_t> stPT(ncand + 1);
-        vc_envelope_line(in, 1L, ncand, ntgt, stH.data(), stPT.data(), [&](int t, vc_u64 v) { out[t] = v; });
+        std::vector<vc_u64> stkv(ncand + 1);
+        vc_stack_array stk{stkv.data()};
+        vc_envelope_line(in, 1L, ncand, ntgt, stk, [&](int t, vc_u64 v) { out[t] = v; });
     }
 
     // (key, corner) records of one z-slab, as vc_sites_detect_local reports them: corner planes

@@ -21,7 +21,6 @@ def lib():
         L = C.CDLL(SO)
         L.hh_sites.restype = C.c_int64
         L.hh_site_records.restype = C.c_int64
-        L.hh_sep.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64]
         _lib = L
     return _lib
 

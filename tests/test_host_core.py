@@ -57,11 +57,19 @@ def test_envelope_line_random(n, dmax, density):
     assert (hc.envelope(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
 
 
-def test_floor_div_exact():
-    rng = np.random.default_rng(0)
-    L = hc.lib()
-    for num, den in zip(rng.integers(-60_000_000, 60_000_000, 20000), rng.integers(1, 8200, 20000)):
-        assert L.hh_floor_div(int(num), int(den)) == int(num) // int(den)
-    for num in (-1, 0, 1, -8192, 8191, 50_331_648, -50_331_648):
-        for den in (1, 4, 8188, 8192):
-            assert L.hh_floor_div(num, den) == num // den
+@pytest.mark.parametrize("n,levels", [(33, 2), (257, 3), (1025, 2), (2049, 4)])
+def test_envelope_line_touching_parabolas(n, levels):
+    """candidates built so that three and more parabolas meet in one point exactly at a target: the entry
+    that only touches the envelope there must survive the forward scan when it holds the lowest id"""
+    rng = np.random.default_rng(n + levels)
+    for rep in range(3):
+        t0 = int(rng.integers(1, n - 2))
+        p = np.arange(n, dtype=np.int64)
+        base = int((2 * (max(t0, n - t0)) + 3) ** 2 + 64)
+        # all parabolas through (t0, base): D_p = base - (2(t0-p)+1)^2, some pushed up by multiples of 8
+        D = base - (2 * (t0 - p) + 1) ** 2 + 8 * rng.integers(0, levels, n)
+        ids = rng.permutation(60_000_000)[:n].astype(np.uint64)
+        H = (D.astype(np.uint64) << np.uint64(32)) | ids
+        H[rng.random(n) > 0.8] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        out = hc.envelope(H, n - 1)
+        assert np.array_equal(out, _brute_line(H, n - 1))

@@ -19,15 +19,19 @@ def run(name, n, reps=3):
     c.upload_volume(vol)
     ns = c.run_dense()  # warm-up (allocations, local-memory resize)
     c.run_dense()
-    c.profile(True)
-    c.profile_reset()
+    c.synchronize()
     t = time.time()
     for _ in range(reps):
         c.run_dense()
-    wall = (time.time() - t) / reps
+    wall = (time.time() - t) / reps  # run_dense returns after a stream sync; pipelined over worker streams
+    c.profile(True)  # profiling serialises the z-chunk pipeline onto one stream
+    c.profile_reset()
+    for _ in range(reps):
+        c.run_dense()
     rep = c.profile_report()
     tot = sum(v["ms"] for v in rep.values()) / reps
-    print(f"== {name}{n}: sites={ns} gen={gen:.1f}s wall/step={wall*1e3:.2f} ms kernels/step={tot:.2f} ms "
+    import os
+    print(f"== {name}{n} workers={os.environ.get('VC_WORKERS')} zchunk={os.environ.get('VC_ZCHUNK')}: sites={ns} gen={gen:.1f}s wall/step={wall*1e3:.2f} ms kernels/step={tot:.2f} ms "
           f"-> {nx*ny*nz/wall:.3e} v/s (wall) {nx*ny*nz/(tot*1e-3):.3e} v/s (kernel sum)")
     for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"   {k:28s} {v['ms']/reps:9.3f} ms  x{v['launches']//reps}")

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvoxcore_gpu.so")
+# VOXCORE_LIB: development override (kernel variants built side by side by tools/build_variants.py)
+LIB_PATH = os.environ.get("VOXCORE_LIB") or os.path.join(HERE, "lib", "libvoxcore_gpu.so")
 
 VC_OK = 0
 ARR_INSIDE, ARR_ID, ARR_D2X4, ARR_EDGE3, ARR_FACE3, ARR_CUBE, ARR_RADIUS = range(7)

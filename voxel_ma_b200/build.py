@@ -40,12 +40,12 @@ def _stale(target, srcs):
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def _compile(src):
-    obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+def _compile(src, objdir=None, defines=()):
+    obj = os.path.join(objdir or OBJDIR, src.replace(".cu", ".o"))
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + _deps()):
         return obj, ""
-    r = subprocess.run([NVCC, *FLAGS, "-c", path, "-o", obj], capture_output=True, text=True)
+    r = subprocess.run([NVCC, *FLAGS, *defines, "-c", path, "-o", obj], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     return obj, r.stderr
@@ -71,6 +71,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
+
+
+def build_variant(name: str, defines) -> str:
+    """Development aid: the same sources with extra -D flags -> lib/variants/libvoxcore_gpu_<name>.so"""
+    vdir = os.path.join(LIBDIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(lambda s: _compile(s, vdir, tuple(defines)), SOURCES))
+    lib = os.path.join(LIBDIR, "variants", f"libvoxcore_gpu_{name}.so")
+    r = subprocess.run([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", lib, *[o for o, _ in res], "-lcudart_static", "-ldl", "-lrt",
+                        "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 // vc_api.cu -- the extern "C" surface declared in include/voxcore_gpu.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -53,14 +54,14 @@ ProfScope::ProfScope(vc_ctx* ctx, const char* name) : c(ctx)
     };
     a = get();
     b = get();
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, c->cur);
 }
 
 ProfScope::~ProfScope()
 {
     if (!st)
         return;
-    cudaEventRecord(b, c->stream);
+    cudaEventRecord(b, c->cur);
     st->pending.emplace_back(a, b);
     st->launches++;
 }
@@ -112,6 +113,22 @@ extern "C"
             vc_ctx_destroy(c);
             return VC_ERR_CUDA;
         }
+        c->cur = c->stream;
+        if (const char* e = getenv("VC_WORKERS"))
+            c->nworkers = atoi(e);
+        if (const char* e = getenv("VC_ZCHUNK"))
+            c->zchunk = atoi(e);
+        c->nworkers = c->nworkers < 1 ? 1 : (c->nworkers > VC_MAX_WORKERS ? VC_MAX_WORKERS : c->nworkers);
+        c->zchunk = c->zchunk < 1 ? 1 : c->zchunk;
+        bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < c->nworkers; ++i)
+            ok = cudaStreamCreateWithFlags(&c->workers[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok)
+        {
+            vc_ctx_destroy(c);
+            return VC_ERR_CUDA;
+        }
         *out = c;
         return VC_OK;
     }
@@ -127,7 +144,7 @@ extern "C"
         for (auto e : c->ev_pool)
             cudaEventDestroy(e);
         DevBuf* bufs[] = {&c->vol, &c->inside, &c->bits, &c->cand_key, &c->cand_corner, &c->site_key, &c->site_corner,
-                          &c->site_xyz, &c->line_ptr, &c->line_ent, &c->g1, &c->g2, &c->id, &c->d2, &c->edge3,
+                          &c->site_xyz, &c->line_ptr, &c->line_ent, &c->g1, &c->g2, &c->stk, &c->id, &c->d2, &c->edge3,
                           &c->face3, &c->cube, &c->radius, &c->sk0, &c->sk1, &c->sv0, &c->sv1, &c->shist,
                           &c->scratch, &c->cl_ptr, &c->cl_ent, &c->gsites};
         for (auto b : bufs)
@@ -140,6 +157,15 @@ extern "C"
             cudaStreamDestroy(c->s_h2d);
         if (c->s_d2h)
             cudaStreamDestroy(c->s_d2h);
+        for (int i = 0; i < VC_MAX_WORKERS; ++i)
+        {
+            if (c->workers[i])
+                cudaStreamDestroy(c->workers[i]);
+            if (c->ev_join[i])
+                cudaEventDestroy(c->ev_join[i]);
+        }
+        if (c->ev_fork)
+            cudaEventDestroy(c->ev_fork);
         delete c;
     }
 
@@ -453,8 +479,7 @@ extern "C"
         VC_TRY(st_classify(c));
         VC_TRY(st_detect_sites(c));
         VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
-        VC_TRY(st_closest_lattice(c));
-        VC_TRY(st_measures(c, true));
+        VC_TRY(st_closest_measures_pipelined(c, true));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (nsites)
             *nsites = c->nsites;
@@ -577,10 +602,9 @@ extern "C"
         VC_TRY(d2h_after(inside, c->inside.p, nv));
         VC_TRY(st_detect_sites(c));
         VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
-        VC_TRY(st_closest_lattice(c));
+        VC_TRY(st_closest_measures_pipelined(c, radius != nullptr));
         VC_TRY(d2h_after(id, c->id.p, nv * 4));
         VC_TRY(d2h_after(d2x4, c->d2.p, nv * 4));
-        VC_TRY(st_measures(c, radius != nullptr));
         VC_TRY(d2h_after(edge3, c->edge3.p, nv * 12));
         VC_TRY(d2h_after(face3, c->face3.p, nv * 12));
         VC_TRY(d2h_after(cube, c->cube.p, nv * 4));

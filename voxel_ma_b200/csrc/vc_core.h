@@ -28,31 +28,6 @@
 typedef unsigned long long vc_u64; // (uint64_t is unsigned long on LP64; CUDA atomics want unsigned long long)
 #define VC_INF 0xFFFFFFFFFFFFFFFFull
 
-// floor(num / den), den > 0, |num| < 2^27, den < 2^15: float estimate, exact integer fix-up.
-VC_HD int vc_floor_div(int num, int den)
-{
-#if defined(__CUDA_ARCH__)
-    int q = __float2int_rd(__fdividef((float)num, (float)den));
-#else
-    float qf = (float)num / (float)den;
-    int q = (int)qf;
-    if ((float)q > qf)
-        --q;
-#endif
-    int r = num - q * den;
-    while (r < 0)
-    {
-        --q;
-        r += den;
-    }
-    while (r >= den)
-    {
-        ++q;
-        r -= den;
-    }
-    return q;
-}
-
 // value of candidate (position p on the corner axis, word H) at target vertex t on that axis
 VC_HD vc_u64 vc_eval(vc_u64 H, int p, int t)
 {
@@ -60,103 +35,139 @@ VC_HD vc_u64 vc_eval(vc_u64 H, int p, int t)
     return H + ((vc_u64)(uint32_t)(d * d) << 32);
 }
 
-// First target t at which candidate k (position pk > pi) is lexicographically better than
-// candidate i.  With u = 2t+1-pi-pk, m = 4(pk-pi), A = D_k - D_i:
-//     f_k(t) - f_i(t) = A - m*u,   so k wins  <=>  m*u > A + e,  e = (id_k - id_i) * 2^-32.
-// floor((A+e)/m) = floor((A - [id_k < id_i]) / m), hence t >= ceil((F + pi + pk) / 2).
-// (A tie in distance goes to the lower id: this is where the reference's tie rule lives.)
-VC_HD int vc_sep(int pi, vc_u64 Hi, int pk, vc_u64 Hk)
-{
-    int A = (int)(uint32_t)(Hk >> 32) - (int)(uint32_t)(Hi >> 32);
-    int c = ((uint32_t)Hk < (uint32_t)Hi) ? 1 : 0;
-    int F = vc_floor_div(A - c, 4 * (pk - pi));
-    return (F + pi + pk + 1) >> 1; // arithmetic shift: floor((x+1)/2) = ceil(x/2)
-}
-
 // One line of the separable transform: lower envelope of the candidates in[j*stride], j in
-// [0,ncand), evaluated at targets t in [0,ntgt).  The forward scan keeps the envelope as a stack of
-// (word, position, first target it wins); its two upper entries live in registers (top, sec), the
-// rest in stH/stPT (thread-local memory on the device), so a pop is a register move plus a load
-// whose result is not needed before the NEXT pop -- the dependent chain never waits on memory.
-// The backward scan emits targets ntgt-1 .. 0 through `emit(t, value)`.
+// [0,ncand), evaluated at targets t in [0,ntgt); `emit(t, value)` is called for t = ntgt-1 .. 0.
 //
-// The candidates are fetched VC_PF at a time into two register banks that alternate: while one
-// bank is consumed the loads of the next are already in flight, so a thread keeps up to 2*VC_PF
-// independent 8-byte loads outstanding instead of one.
+// In the doubled coordinate x = 2t+1 a candidate at position p is the parabola
+//     f_p(x) = D_p + (x - 2p)^2 ,      g_p := D_p + 4 p^2 ,
+// all of the same curvature, so two of them cross exactly once, at x_ab = (g_b - g_a) / (4 (b - a)),
+// and the lower envelope visits the surviving candidates in position order.
+//
+// Forward scan (Maurer-style, integers only -- no division, no stored break points): the stack
+// holds the candidates of the envelope so far.  With u < v the two upper entries and w the new
+// candidate, v is STRICTLY hidden (above min(f_u, f_w) everywhere) iff x_uv > x_vw, i.e.
+//     (g_v - g_u) (w - v)  >  (g_w - g_v) (v - u)          (64-bit products, |.| < 2^40)
+// and only then is it dropped; a candidate that merely touches the envelope in one point stays,
+// because at that point it may hold the lowest site id.
+// Backward scan: at target t the winner is the top unless the entry below is at least as close;
+// while  D_sec(t) <= D_best(t)  the top is popped (left of the crossing it never wins again) and
+// the minimum is taken on the full (distance, id) words -- which is exactly where the
+// reference's tie rule (3rdparty/ann/src/brute.cpp:56-82: equal distance -> lowest id) lives.
+//
+// Memory behaviour is what bounds this scan (one thread per line, a dependent chain per step), so:
+//   - stack: the two upper entries live in registers; the rest is a per-line array of packed
+//     8-byte entries  D << 38 | id << 12 | p  (D < 2^26, id < 2^26, p < 2^12), CONTIGUOUS per line, so
+//     consecutive pops of a thread hit the same 32-byte sector.  (A thread-local CUDA array would
+//     interleave the 32 lanes of a warp word by word: lanes at different depths then touch 32
+//     different sectors per access.)
+//   - candidates: fetched VC_PF at a time into two register banks that alternate (the loads of the
+//     next bank are in flight while one is consumed), and requested into L2 VC_PF_L2 candidates
+//     ahead.
+#ifndef VC_PF
 #define VC_PF 4
+#endif
+#ifndef VC_PF_L2
+#define VC_PF_L2 48
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define VC_LOAD_STREAM(p) __ldcs(p) // read once: evict-first
+#define VC_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 #define VC_LOAD_STREAM(p) (*(p))
+#define VC_PREFETCH_L2(p) ((void)0)
 #endif
+
+#define VC_MAX_SITE_ID ((1 << 26) - 1) // ids must fit the packed stack entry
 
 struct vc_env_state
 {
-    int q;        // index of the top entry; -1 = empty.  entry q = top, q-1 = sec, 0..q-2 in memory
-    vc_u64 Hs;    // top
-    int ps, ts;
-    vc_u64 H2;    // second
-    int p2, t2;
+    int q;              // index of the top entry; -1 = empty.  entry q = top, q-1 = sec, 0..q-2 in memory
+    vc_u64 Ht, Hs;      // words of top / second
+    int pt, ps;         // positions
+    int gt, gs;         // g = D + 4 p^2
 };
 
-VC_HD void vc_env_pop(vc_env_state& s, const vc_u64* stH, const uint32_t* stPT)
+VC_HD vc_u64 vc_ent_pack(vc_u64 H, int p)
+{
+    return ((H >> 32) << 38) | ((vc_u64)(uint32_t)H << 12) | (vc_u64)(uint32_t)p;
+}
+
+// Storage of the stack entries below the two in registers (depth d = 0 .. q-2).  The scan is written
+// against this small interface so the device can keep the upper entries in shared memory
+// (vc_edt.cu: StackRing) while the CPU test harness uses a plain array.
+//   store(d, e)      entry at depth d := e          (forward scan, d = current storage top + 1)
+//   load(d)          entry at depth d               (forward scan pops)
+//   begin_drain(d)   the backward scan starts: depths d, d-1, ... 0 will be read in that order
+//   drain(d)         entry at depth d, in drain order
+struct vc_stack_array
+{
+    vc_u64* a;
+    VC_HD void store(int d, vc_u64 e) { a[d] = e; }
+    VC_HD vc_u64 load(int d) { return a[d]; }
+    VC_HD void begin_drain(int) {}
+    VC_HD vc_u64 drain(int d) { return a[d]; }
+};
+
+template <bool DRAIN, class Stack>
+VC_HD void vc_env_pop(vc_env_state& s, Stack& stk)
 {
     --s.q;
-    s.Hs = s.H2;
-    s.ps = s.p2;
-    s.ts = s.t2;
+    s.Ht = s.Hs;
+    s.pt = s.ps;
+    s.gt = s.gs;
     if (s.q >= 1)
     {
-        s.H2 = stH[s.q - 1];
-        uint32_t pt = stPT[s.q - 1];
-        s.p2 = (int)(pt & 0xFFFFu);
-        s.t2 = (int)(pt >> 16);
+        vc_u64 e = DRAIN ? stk.drain(s.q - 1) : stk.load(s.q - 1);
+        s.ps = (int)(e & 0xFFFu);
+        s.Hs = ((e >> 38) << 32) | ((e >> 12) & 0x3FFFFFFu);
+        s.gs = (int)(e >> 38) + 4 * s.ps * s.ps;
     }
 }
 
-VC_HD void vc_env_push(vc_env_state& s, vc_u64 H, int j, int ntgt, vc_u64* stH, uint32_t* stPT)
+template <class Stack>
+VC_HD void vc_env_push(vc_env_state& s, vc_u64 H, int j, Stack& stk)
 {
     if (H == VC_INF)
         return;
-    // the top loses already where its interval starts: it wins nowhere
-    while (s.q >= 0 && vc_eval(s.Hs, s.ps, s.ts) > vc_eval(H, j, s.ts))
-        vc_env_pop(s, stH, stPT);
-    int w = 0;
+    const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
+    while (s.q >= 1 &&
+           (long long)(s.gt - s.gs) * (long long)(j - s.pt) > (long long)(g - s.gt) * (long long)(s.pt - s.ps))
+        vc_env_pop<false>(s, stk); // top strictly hidden by (second, new)
+    if (s.q >= 1)
+        stk.store(s.q - 1, vc_ent_pack(s.Hs, s.ps));
     if (s.q >= 0)
     {
-        w = vc_sep(s.ps, s.Hs, j, H);
-        if (w >= ntgt)
-            return; // wins only beyond the last target
-        if (s.q >= 1)
-        {
-            stH[s.q - 1] = s.H2;
-            stPT[s.q - 1] = (uint32_t)s.p2 | ((uint32_t)s.t2 << 16);
-        }
-        s.H2 = s.Hs;
-        s.p2 = s.ps;
-        s.t2 = s.ts;
+        s.Hs = s.Ht;
+        s.ps = s.pt;
+        s.gs = s.gt;
     }
     ++s.q;
-    s.Hs = H;
-    s.ps = j;
-    s.ts = w;
+    s.Ht = H;
+    s.pt = j;
+    s.gt = g;
 }
 
-template <class Emit>
-VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt,
-                            vc_u64* stH, uint32_t* stPT, Emit emit)
+template <class Stack, class Emit>
+VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt, Stack& stk, Emit emit)
 {
     vc_env_state s;
     s.q = -1;
-    s.Hs = s.H2 = 0;
-    s.ps = s.ts = s.p2 = s.t2 = 0;
+    s.Ht = s.Hs = 0;
+    s.pt = s.ps = s.gt = s.gs = 0;
     vc_u64 bankA[VC_PF], bankB[VC_PF];
 #define VC_FETCH(bank, j0)                                                                         \
     _Pragma("unroll") for (int k = 0; k < VC_PF; ++k)                                              \
-        bank[k] = ((j0) + k < ncand) ? VC_LOAD_STREAM(in + (long)((j0) + k) * stride) : (vc_u64)VC_INF;
+    {                                                                                              \
+        bank[k] = ((j0) + k < ncand) ? VC_LOAD_STREAM(in + (long)((j0) + k) * stride) : (vc_u64)VC_INF; \
+        if (VC_PF_L2 > 0 && (j0) + k + VC_PF_L2 < ncand)                                           \
+            VC_PREFETCH_L2(in + (long)((j0) + k + VC_PF_L2) * stride);                             \
+    }
 #define VC_CONSUME(bank, j0)                                                                       \
-    _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) vc_env_push(s, bank[k], (j0) + k, ntgt, stH, stPT);
+    _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) vc_env_push(s, bank[k], (j0) + k, stk);
+    if (VC_PF_L2 > 0)
+        for (int j = 0; j < VC_PF_L2 && j < ncand; ++j)
+            VC_PREFETCH_L2(in + (long)j * stride);
     VC_FETCH(bankA, 0)
     for (int j0 = 0; j0 < ncand; j0 += 2 * VC_PF)
     {
@@ -170,11 +181,23 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
     // one uniform backward loop (a line without candidates emits VC_INF) so that a warp whose
     // lanes each own a line stays convergent at the emit() call and may synchronise inside it
     const bool empty = s.q < 0;
+    stk.begin_drain(s.q - 2);
     for (int t = ntgt - 1; t >= 0; --t)
     {
-        emit(t, empty ? (vc_u64)VC_INF : vc_eval(s.Hs, s.ps, t));
-        if (t == s.ts && s.q > 0)
-            vc_env_pop(s, stH, stPT);
+        vc_u64 best = VC_INF;
+        if (!empty)
+        {
+            best = vc_eval(s.Ht, s.pt, t);
+            while (s.q > 0)
+            {
+                const vc_u64 vs = vc_eval(s.Hs, s.ps, t);
+                if ((uint32_t)(vs >> 32) > (uint32_t)(best >> 32))
+                    break;
+                best = vs < best ? vs : best;
+                vc_env_pop<true>(s, stk);
+            }
+        }
+        emit(t, best);
     }
 }
 

@@ -14,6 +14,8 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 typedef unsigned char u8;
 
+#define VC_MAX_WORKERS 16
+
 struct DevBuf
 {
     void* p = nullptr;
@@ -56,10 +58,17 @@ struct vc_ctx
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // z-chunk pipeline: the closest-site passes and the measures of different z chunks run on
+    // worker streams so that the tail of one stage overlaps the next stage of another chunk
+    cudaStream_t cur = nullptr;            // stream VC_LAUNCH uses (== stream outside the pipeline)
+    cudaStream_t workers[VC_MAX_WORKERS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[VC_MAX_WORKERS] = {};
+    int nworkers = 4, zchunk = 32;
     // grid: global size, owned vertex planes [z0,z1), closest planes [z0,zc), resident voxel planes [zlo,zhi)
     int nx = 0, ny = 0, nz = 0, z0 = 0, z1 = 0, zc = 0, zlo = 0, zhi = 0;
     bool have_grid = false, have_vol = false, have_inside = false, have_sites = false, have_closest = false,
          have_measures = false;
+    bool attr_measures = false; // dynamic shared memory opt-in done for this device
     bool lattice = true; // sites lie on the corner lattice -> dense transform
     DevBuf vol, inside;
     DevBuf bits; // occupancy bit rows: u32[(z - zlo) * ny + y][wr], bit x & 31 of word x >> 5; wr = nx / 32 + 1
@@ -72,6 +81,7 @@ struct vc_ctx
     DevBuf line_ptr, line_ent; // z-line lists: int32[(nx+1)(ny+1)+1], u64 (cz<<32|id)
     // transform scratch + results
     DevBuf g1, g2, id, d2, edge3, face3, cube, radius;
+    DevBuf stk; // envelope stacks of the transform passes (packed u64 per line and depth)
     // sort scratch
     DevBuf sk0, sk1, sv0, sv1, shist;
     DevBuf scratch; // small device scratch (counters)
@@ -119,7 +129,7 @@ struct ProfScope
     do                                                                 \
     {                                                                  \
         ProfScope _ps((c), (name));                                    \
-        kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);   \
+        kern<<<(grid), (block), (smem), (c)->cur>>>(__VA_ARGS__);   \
     } while (0)
 
 static inline unsigned vc_blocks(size_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -140,6 +150,12 @@ int st_detect_sites(vc_ctx* c);
 int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key);
 int st_closest_lattice(vc_ctx* c);
 int st_measures(vc_ctx* c, bool want_radius);
+// the two stages above for the whole slab, z chunk by z chunk on the worker streams
+int st_closest_measures_pipelined(vc_ctx* c, bool want_radius);
+// building blocks: planes [zb,ze) of the slab on stream c->cur
+int edt_range(vc_ctx* c, int zb, int ze, int region, int region_planes);
+int measures_range(vc_ctx* c, int za, int zb, bool want_radius);
+int measures_alloc(vc_ctx* c, bool want_radius);
 int st_classify_points(vc_ctx* c, const float* xyz, int64_t n, const double* M, uint8_t* out);
 int st_face_lambda(vc_ctx* c, const int32_t* pairs, int64_t nf, float* out);
 int st_vertex_radii(vc_ctx* c, const float* v, int64_t nv, const int32_t* site_of_v, float* out);

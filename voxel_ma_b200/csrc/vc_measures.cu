@@ -24,23 +24,32 @@ __device__ __forceinline__ float vc_dist2f(float ax, float ay, float az, float b
 // so max over edges of sqrt(d2) == sqrt(max d2): the 12 edge terms are reduced as squared
 // distances and only the 7 outputs (+ radius) take a square root.
 //
-// A block owns a 32 x 8 (x,y) tile and marches up a chunk of z planes.  Per plane it fetches the
-// (32+1) x (8+1) ids once (id 4 B + flag 1 B per vertex: the algorithmic read), gathers each id's
-// site from the L2-resident table once, and parks (site, flags) in shared memory; a thread keeps
-// the 4 records of its own column for plane z in registers and reads the 4 of plane z+1 from
-// shared memory, so the 8 x 4 B outputs per vertex are the only HBM traffic that scales.
-// The id / flag loads of plane z+2 are issued before plane z+1 is consumed.
-// id: planes [z0, zc) (zc = z1+1 halo when z1 < nz); inside: planes [zlo, zhi).
+// Work split.  A thread owns 4 consecutive x vertices of one row, so every access to the
+// per-vertex planes is one 128-bit load / store (8 stores per 4 vertices).  A block owns a
+// 128 x 8 (x,y) tile and marches up a chunk of z planes; per plane it parks one 16-byte record
+// (site position, flags) per tile vertex (+ a one-vertex halo in x and y) in shared memory,
+// in a ring of three plane buffers (a plane is read by the
+// iterations z-1 and z, so one barrier per plane suffices with three).
+// What is skipped.  A cell is valid only if ALL its vertices are inside, and every one of the 7
+// cells anchored at v contains v: so an outside vertex reports 0 everywhere, its site is never
+// used by any cell, and neither its id nor its site record is fetched at all.  The occupancy bit
+// rows (1 bit / vertex) decide; ids are read (and sites gathered from the L2-resident table, once
+// per vertex) only for 4-vertex groups that contain an inside vertex.
+// Radius.  r(v) = dist(site, v) in float32.  For lattice sites every term of trimesh::dist2 is an
+// exact multiple of 1/4, so while 4*d^2 < 2^24 the float sum equals (float)(4d^2)/4 exactly and the
+// radius comes from the d2x4 plane (one more 128-bit load) instead of a gather; beyond that, and
+// for arbitrary site sets, the site is fetched and the sum is accumulated in the reference order.
+// id, d2: planes [z0, zc) (zc = z1+1 halo when z1 < nz); bits: planes [zlo, zhi).
 // =============================================================================================
-#define CM_TX 32
-#define CM_TY 8
-#define CM_ENT ((CM_TX + 1) * (CM_TY + 1)) // 297 records per plane
-#define CM_PER ((CM_ENT + CM_TX * CM_TY - 1) / (CM_TX * CM_TY)) // records a thread loads per plane (2)
+#define CM_VX 4                 // vertices per thread along x
+#define CM_TW (32 * CM_VX)      // tile width  (x)
+#define CM_TH 8                 // tile height (y)
+#define CM_PITCH (CM_TW + 4)    // record row pitch (halo column + padding)
 
 struct CmRec
 {
     float x, y, z;
-    u32 f; // bit 0: vertex exists and has a site; bit 1: vertex is inside
+    u32 f; // bit 0: vertex has a site; bit 1: vertex is inside (records of outside vertices hold f = 0)
 };
 
 __device__ __forceinline__ float cm_e2(const CmRec& a, const CmRec& b)
@@ -48,164 +57,269 @@ __device__ __forceinline__ float cm_e2(const CmRec& a, const CmRec& b)
     return (a.f & b.f & 1u) ? vc_dist2f(a.x, a.y, a.z, b.x, b.y, b.z) : 0.0f;
 }
 
-__global__ void __launch_bounds__(CM_TX* CM_TY, 4)
-    k_cell_measures(const int* __restrict__ id, const u8* __restrict__ inside, const float4* __restrict__ site,
-                    int nx, int ny, int z0, int z1, int zc, int zlo, int zchunk, float* __restrict__ edge3,
-                    float* __restrict__ face3, float* __restrict__ cube, float* __restrict__ radius)
+template <bool VEC>
+__global__ void __launch_bounds__(32 * CM_TH, 3)
+    k_cell_measures(const int* __restrict__ id, const u32* __restrict__ d2x4, const u32* __restrict__ bits, int wr,
+                    const float4* __restrict__ site, int nx, int ny, int z0, int z1, int zc, int zlo, int za, int zb, int zchunk,
+                    int radius_from_d2, float* __restrict__ edge3, float* __restrict__ face3, float* __restrict__ cube,
+                    float* __restrict__ radius)
 {
-    __shared__ float4 tile[2][CM_TY + 1][CM_TX + 1];
-    const int tx = threadIdx.x & (CM_TX - 1), ty = threadIdx.x / CM_TX;
-    const int x0 = blockIdx.x * CM_TX, y0 = blockIdx.y * CM_TY;
-    const int zs = z0 + blockIdx.z * zchunk, ze = min(zs + zchunk, z1);
-    const int x = x0 + tx, y = y0 + ty;
+    extern __shared__ float4 cm_tile[]; // [3][CM_TH + 1][CM_PITCH]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * CM_TW, y0 = blockIdx.y * CM_TH;
+    const int zs = za + blockIdx.z * zchunk, ze = min(zs + zchunk, zb); // anchors [za, zb) of the slab [z0, z1)
+    const int x = x0 + CM_VX * tx, y = y0 + ty;
     const size_t plane = (size_t)nx * ny;
     const size_t nv = plane * (size_t)(z1 - z0);
+    auto tile = [&](int buf, int row, int col) -> float4& { return cm_tile[(buf * (CM_TH + 1) + row) * CM_PITCH + col]; };
 
-    // the records this thread loads each plane: e = threadIdx.x + k*256 -> (hy, hx) of the halo tile
-    size_t lo[CM_PER];
-    int hyx[CM_PER];
-    bool lok[CM_PER];
-#pragma unroll
-    for (int k = 0; k < CM_PER; ++k)
+    // inside nibble of the 4 vertices (xx .. xx+3, yy, zz); 0 outside the grid / beyond the halo plane
+    auto nibble = [&](int xx, int yy, int zz) -> u32
     {
-        int e = threadIdx.x + k * CM_TX * CM_TY;
-        int hy = e / (CM_TX + 1), hx = e - hy * (CM_TX + 1);
-        lok[k] = e < CM_ENT && x0 + hx < nx && y0 + hy < ny;
-        hyx[k] = e < CM_ENT ? hy * (CM_TX + 1) + hx : -1;
-        lo[k] = (size_t)(x0 + hx) + (size_t)nx * (size_t)(y0 + hy);
-    }
-    int sid[CM_PER];
-    u32 fin[CM_PER];
-    auto fetch_ids = [&](int zz)
+        if (xx >= nx || yy >= ny || zz >= zc)
+            return 0u;
+        u32 w = __ldg(bits + ((size_t)(zz - zlo) * ny + yy) * (size_t)wr + (xx >> 5));
+        return (w >> (xx & 31)) & 0xFu; // xx is a multiple of 4: the nibble never straddles a word
+    };
+    // park the records of the 4 vertices (xx.., yy, zz) whose inside nibble is `nib`
+    auto park4 = [&](int buf, int row, int col, int xx, int yy, int zz, u32 nib)
     {
+        float4 r[CM_VX];
 #pragma unroll
-        for (int k = 0; k < CM_PER; ++k)
+        for (int k = 0; k < CM_VX; ++k)
+            r[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (nib)
         {
-            sid[k] = -1;
-            fin[k] = 0;
-            if (lok[k] && zz < zc)
+            const size_t o = (size_t)xx + (size_t)nx * (size_t)yy + plane * (size_t)(zz - z0);
+            int s[CM_VX];
+            if (VEC)
             {
-                sid[k] = __ldcs(id + lo[k] + plane * (size_t)(zz - z0));
-                fin[k] = __ldg(inside + lo[k] + plane * (size_t)(zz - zlo)) ? 2u : 0u;
+                int4 v = __ldcs(reinterpret_cast<const int4*>(id + o));
+                s[0] = v.x, s[1] = v.y, s[2] = v.z, s[3] = v.w;
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < CM_VX; ++k)
+                    s[k] = (xx + k < nx) ? __ldcs(id + o + k) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < CM_VX; ++k)
+                if ((nib >> k) & 1u)
+                {
+                    u32 f = 2u;
+                    if (s[k] >= 0)
+                    {
+                        r[k] = __ldg(site + s[k]);
+                        f = 3u;
+                    }
+                    r[k].w = __uint_as_float(f);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < CM_VX; ++k)
+            tile(buf, row, col + k) = r[k];
+    };
+    // one plane of records: own row, the halo row (warp 0), the halo column (lane 31 of each row)
+    auto park_plane = [&](int buf, int zz, u32 nib_own)
+    {
+        park4(buf, ty, CM_VX * tx, x, y, zz, nib_own);
+        if (ty == 0)
+            park4(buf, CM_TH, CM_VX * tx, x, y0 + CM_TH, zz, nibble(x, y0 + CM_TH, zz));
+        if (tx == 31)
+        {
+            const int nrow = ty == 0 ? 2 : 1; // row ty, and the corner for ty == 0
+            for (int j = 0; j < nrow; ++j)
+            {
+                const int row = j == 0 ? ty : CM_TH;
+                const int xx = x0 + CM_TW, yy = y0 + row;
+                float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (xx < nx && yy < ny && zz < zc)
+                {
+                    u32 w = __ldg(bits + ((size_t)(zz - zlo) * ny + yy) * (size_t)wr + (xx >> 5));
+                    if ((w >> (xx & 31)) & 1u)
+                    {
+                        int sid = __ldg(id + (size_t)xx + (size_t)nx * (size_t)yy + plane * (size_t)(zz - z0));
+                        u32 f = 2u;
+                        if (sid >= 0)
+                        {
+                            r = __ldg(site + sid);
+                            f = 3u;
+                        }
+                        r.w = __uint_as_float(f);
+                    }
+                }
+                tile(buf, row, CM_TW) = r;
             }
         }
     };
-    auto park = [&](int buf)
+    auto rec = [&](int buf, int row, int col) -> CmRec
     {
-#pragma unroll
-        for (int k = 0; k < CM_PER; ++k)
-            if (hyx[k] >= 0)
-            {
-                float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                u32 f = fin[k];
-                if (sid[k] >= 0)
-                {
-                    r = __ldg(site + sid[k]);
-                    f |= 1u;
-                }
-                r.w = __uint_as_float(f);
-                (&tile[buf][0][0])[hyx[k]] = r;
-            }
-    };
-    auto rec = [&](int buf, int dy, int dx) -> CmRec
-    {
-        float4 v = tile[buf][ty + dy][tx + dx];
+        float4 v = tile(buf, row, col);
         CmRec r;
-        r.x = v.x;
-        r.y = v.y;
-        r.z = v.z;
+        r.x = v.x, r.y = v.y, r.z = v.z;
         r.f = __float_as_uint(v.w);
         return r;
     };
 
-    fetch_ids(zs);
-    park(0);
-    fetch_ids(zs + 1);
-    __syncthreads();
-    CmRec a0 = rec(0, 0, 0), a1 = rec(0, 0, 1), a2 = rec(0, 1, 0), a3 = rec(0, 1, 1);
-    // Every one of the 7 cells anchored at v contains v, so a vertex outside the solid reports 0 for
-    // all of them and none of its edge terms is ever used: the distance arithmetic runs only for
-    // inside anchors (in-plane edges of plane z+1 are computed when that plane's anchor is inside,
-    // and carried over to the next iteration).
-    float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;
-    if (a0.f & 2u)
-    {
-        ex0 = cm_e2(a0, a1);
-        ex1 = cm_e2(a2, a3);
-        ey0 = cm_e2(a0, a2);
-        ey1 = cm_e2(a1, a3);
-    }
-    const bool live = x < nx && y < ny;
+    u32 nib_cur = nibble(x, y, zs);
+    park_plane(0, zs, nib_cur);
+    const bool row_live = y < ny && x < nx;
     size_t o = (size_t)x + (size_t)nx * (size_t)y + plane * (size_t)(zs - z0);
     for (int z = zs; z < ze; ++z, o += plane)
     {
-        const int buf = (z - zs + 1) & 1;
-        park(buf);          // plane z+1 (ids fetched one iteration ago)
-        fetch_ids(z + 2);   // in flight while plane z is computed
+        const int bufa = (z - zs) % 3, bufb = (z - zs + 1) % 3;
+        const u32 nib_next = nibble(x, y, z + 1);
+        park_plane(bufb, z + 1, nib_next);
         __syncthreads();
-        const CmRec b0 = rec(buf, 0, 0), b1 = rec(buf, 0, 1), b2 = rec(buf, 1, 0), b3 = rec(buf, 1, 1);
-        // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
-        float ex2 = 0.0f, ex3 = 0.0f, ey2 = 0.0f, ey3 = 0.0f;
-        if ((a0.f | b0.f) & 2u)
+        float le[3][CM_VX], lf[3][CM_VX], lc[CM_VX], lr[CM_VX];
+#pragma unroll
+        for (int k = 0; k < CM_VX; ++k)
+            le[0][k] = le[1][k] = le[2][k] = lf[0][k] = lf[1][k] = lf[2][k] = lc[k] = lr[k] = 0.0f;
+        if (nib_cur)
         {
-            ex2 = cm_e2(b0, b1);
-            ex3 = cm_e2(b2, b3);
-            ey2 = cm_e2(b0, b2);
-            ey3 = cm_e2(b1, b3);
+#pragma unroll
+            for (int k = 0; k < CM_VX; ++k)
+                if ((nib_cur >> k) & 1u)
+                {
+                    const int c0 = CM_VX * tx + k;
+                    const CmRec a0 = rec(bufa, ty, c0), a1 = rec(bufa, ty, c0 + 1), a2 = rec(bufa, ty + 1, c0),
+                                a3 = rec(bufa, ty + 1, c0 + 1);
+                    const CmRec b0 = rec(bufb, ty, c0), b1 = rec(bufb, ty, c0 + 1), b2 = rec(bufb, ty + 1, c0),
+                                b3 = rec(bufb, ty + 1, c0 + 1);
+                    // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
+                    const float ex0 = cm_e2(a0, a1), ex1 = cm_e2(a2, a3), ex2 = cm_e2(b0, b1), ex3 = cm_e2(b2, b3);
+                    const float ey0 = cm_e2(a0, a2), ey1 = cm_e2(a1, a3), ey2 = cm_e2(b0, b2), ey3 = cm_e2(b1, b3);
+                    const float w0 = cm_e2(a0, b0), w1 = cm_e2(a1, b1), w2 = cm_e2(a2, b2), w3 = cm_e2(a3, b3);
+                    const u32 i1 = a1.f & 2u, i2 = a2.f & 2u, i3 = a3.f & 2u;
+                    const u32 i4 = b0.f & 2u, i5 = b1.f & 2u, i6 = b2.f & 2u, i7 = b3.f & 2u;
+                    if (i1)
+                        le[0][k] = __fsqrt_rn(ex0);
+                    if (i2)
+                        le[1][k] = __fsqrt_rn(ey0);
+                    if (i4)
+                        le[2][k] = __fsqrt_rn(w0);
+                    if (i1 & i2 & i3)
+                        lf[0][k] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1)));
+                    if (i1 & i4 & i5)
+                        lf[1][k] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex2), fmaxf(w0, w1)));
+                    if (i2 & i4 & i6)
+                        lf[2][k] = __fsqrt_rn(fmaxf(fmaxf(ey0, ey2), fmaxf(w0, w2)));
+                    if (i1 & i2 & i3 & i4 & i5 & i6 & i7)
+                    {
+                        float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
+                        lc[k] = __fsqrt_rn(fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3))));
+                    }
+                }
         }
-        float le0 = 0.0f, le1 = 0.0f, le2 = 0.0f, lf0 = 0.0f, lf1 = 0.0f, lf2 = 0.0f, lc = 0.0f;
-        if (a0.f & 2u)
+        if (row_live)
         {
-            const float w0 = cm_e2(a0, b0), w1 = cm_e2(a1, b1), w2 = cm_e2(a2, b2), w3 = cm_e2(a3, b3);
-            const u32 i1 = a1.f & 2u, i2 = a2.f & 2u, i3 = a3.f & 2u;
-            const u32 i4 = b0.f & 2u, i5 = b1.f & 2u, i6 = b2.f & 2u, i7 = b3.f & 2u;
-            if (i1)
-                le0 = __fsqrt_rn(ex0);
-            if (i2)
-                le1 = __fsqrt_rn(ey0);
-            if (i4)
-                le2 = __fsqrt_rn(w0);
-            if (i1 & i2 & i3)
-                lf0 = __fsqrt_rn(fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1)));
-            if (i1 & i4 & i5)
-                lf1 = __fsqrt_rn(fmaxf(fmaxf(ex0, ex2), fmaxf(w0, w1)));
-            if (i2 & i4 & i6)
-                lf2 = __fsqrt_rn(fmaxf(fmaxf(ey0, ey2), fmaxf(w0, w2)));
-            if (i1 & i2 & i3 & i4 & i5 & i6 & i7)
+            if (radius)
             {
-                float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
-                lc = __fsqrt_rn(fmaxf(m, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3))));
+                u32 q[CM_VX];
+                if (VEC)
+                {
+                    uint4 v = __ldcs(reinterpret_cast<const uint4*>(d2x4 + o));
+                    q[0] = v.x, q[1] = v.y, q[2] = v.z, q[3] = v.w;
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < CM_VX; ++k)
+                        q[k] = (x + k < nx) ? __ldcs(d2x4 + o + k) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < CM_VX; ++k)
+                {
+                    if (radius_from_d2 && q[k] < (1u << 24))
+                        lr[k] = __fsqrt_rn(__fmul_rn((float)q[k], 0.25f));
+                    else if (x + k < nx)
+                    { // rare: far beyond 2048 voxels, or an arbitrary site set -- the reference's own sum
+                        int sid = __ldg(id + o + k);
+                        if (sid >= 0)
+                        {
+                            float4 sp = __ldg(site + sid);
+                            lr[k] = __fsqrt_rn(vc_dist2f(sp.x, sp.y, sp.z, (float)(x + k), (float)y, (float)z));
+                        }
+                    }
+                }
             }
-        }
-        if (live)
-        {
+            auto put = [&](float* base, const float* v)
+            {
+                if (VEC)
+                    __stcs(reinterpret_cast<float4*>(base + o), make_float4(v[0], v[1], v[2], v[3]));
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < CM_VX; ++k)
+                        if (x + k < nx)
+                            __stcs(base + o + k, v[k]);
+                }
+            };
             if (edge3)
             {
-                __stcs(edge3 + o, le0);
-                __stcs(edge3 + nv + o, le1);
-                __stcs(edge3 + 2 * nv + o, le2);
+                put(edge3, le[0]);
+                put(edge3 + nv, le[1]);
+                put(edge3 + 2 * nv, le[2]);
             }
             if (face3)
             {
-                __stcs(face3 + o, lf0);
-                __stcs(face3 + nv + o, lf1);
-                __stcs(face3 + 2 * nv + o, lf2);
+                put(face3, lf[0]);
+                put(face3 + nv, lf[1]);
+                put(face3 + 2 * nv, lf[2]);
             }
             if (cube)
-                __stcs(cube + o, lc);
+                put(cube, lc);
             if (radius)
-                __stcs(radius + o,
-                       (a0.f & 1u) ? __fsqrt_rn(vc_dist2f(a0.x, a0.y, a0.z, (float)x, (float)y, (float)z)) : 0.0f);
+                put(radius, lr);
         }
-        a0 = b0;
-        a1 = b1;
-        a2 = b2;
-        a3 = b3;
-        ex0 = ex2;
-        ex1 = ex3;
-        ey0 = ey2;
-        ey1 = ey3;
+        nib_cur = nib_next;
     }
+}
+
+int measures_alloc(vc_ctx* c, bool want_radius)
+{
+    const size_t nv = (size_t)c->nx * c->ny * (size_t)(c->z1 - c->z0);
+    VC_CUDA(c, c->edge3.ensure(nv * 3 * 4));
+    VC_CUDA(c, c->face3.ensure(nv * 3 * 4));
+    VC_CUDA(c, c->cube.ensure(nv * 4));
+    if (want_radius)
+        VC_CUDA(c, c->radius.ensure(nv * 4));
+    const size_t smem = (size_t)3 * (CM_TH + 1) * CM_PITCH * sizeof(float4);
+    if (!c->attr_measures)
+    {
+        VC_CUDA(c, cudaFuncSetAttribute(k_cell_measures<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VC_CUDA(c, cudaFuncSetAttribute(k_cell_measures<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->attr_measures = true;
+    }
+    return VC_OK;
+}
+
+// measures of the anchor planes [za, zb) of the slab, on stream c->cur (buffers from measures_alloc)
+int measures_range(vc_ctx* c, int za, int zb, bool want_radius)
+{
+    // z chunks per block: long enough to amortise the one extra plane a block loads, short enough that
+    // the grid is several waves of the SMs
+    const int nplanes = zb - za;
+    const unsigned gx = (c->nx + CM_TW - 1) / CM_TW, gy = (c->ny + CM_TH - 1) / CM_TH;
+    int zchunk = 32;
+    while (zchunk > 4 && (size_t)gx * gy * ((nplanes + zchunk - 1) / zchunk) < (size_t)c->sm_count * 16)
+        zchunk >>= 1;
+    dim3 grid(gx, gy, (nplanes + zchunk - 1) / zchunk);
+    if (grid.y > 65535u || grid.z > 65535u)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "grid too large for the measures kernel");
+    const size_t smem = (size_t)3 * (CM_TH + 1) * CM_PITCH * sizeof(float4);
+    if ((c->nx & 3) == 0)
+        VC_LAUNCH(c, "cell_measures", k_cell_measures<true>, grid, 32 * CM_TH, smem, c->id.as<int>(), c->d2.as<u32>(),
+                  c->bits.as<u32>(), c->wr, c->site_xyz.as<float4>(), c->nx, c->ny, c->z0, c->z1, c->zc, c->zlo, za, zb,
+                  zchunk, c->lattice ? 1 : 0, c->edge3.as<float>(), c->face3.as<float>(), c->cube.as<float>(),
+                  want_radius ? c->radius.as<float>() : nullptr);
+    else
+        VC_LAUNCH(c, "cell_measures", k_cell_measures<false>, grid, 32 * CM_TH, smem, c->id.as<int>(), c->d2.as<u32>(),
+                  c->bits.as<u32>(), c->wr, c->site_xyz.as<float4>(), c->nx, c->ny, c->z0, c->z1, c->zc, c->zlo, za, zb,
+                  zchunk, c->lattice ? 1 : 0, c->edge3.as<float>(), c->face3.as<float>(), c->cube.as<float>(),
+                  want_radius ? c->radius.as<float>() : nullptr);
+    return VC_OK;
 }
 
 int st_measures(vc_ctx* c, bool want_radius)
@@ -214,25 +328,8 @@ int st_measures(vc_ctx* c, bool want_radius)
         return vc_fail(c, VC_ERR_STATE, "vc_cell_measures_grid needs vc_classify_grid and vc_closest_grid");
     if (c->zhi < c->zc)
         return vc_fail(c, VC_ERR_STATE, "inside flags do not cover the halo plane");
-    const size_t nv = (size_t)c->nx * c->ny * (size_t)(c->z1 - c->z0);
-    VC_CUDA(c, c->edge3.ensure(nv * 3 * 4));
-    VC_CUDA(c, c->face3.ensure(nv * 3 * 4));
-    VC_CUDA(c, c->cube.ensure(nv * 4));
-    if (want_radius)
-        VC_CUDA(c, c->radius.ensure(nv * 4));
-    // z chunks: long enough to amortise the one extra plane a chunk loads, short enough that the grid
-    // is several waves of the SMs
-    const int nplanes = c->z1 - c->z0;
-    const unsigned gx = (c->nx + CM_TX - 1) / CM_TX, gy = (c->ny + CM_TY - 1) / CM_TY;
-    int zchunk = 32;
-    while (zchunk > 4 && (size_t)gx * gy * ((nplanes + zchunk - 1) / zchunk) < (size_t)c->sm_count * 16)
-        zchunk >>= 1;
-    dim3 grid(gx, gy, (nplanes + zchunk - 1) / zchunk);
-    if (grid.y > 65535u || grid.z > 65535u)
-        return vc_fail(c, VC_ERR_UNSUPPORTED, "grid too large for the measures kernel");
-    VC_LAUNCH(c, "cell_measures", k_cell_measures, grid, CM_TX * CM_TY, 0, c->id.as<int>(), c->inside.as<u8>(),
-              c->site_xyz.as<float4>(), c->nx, c->ny, c->z0, c->z1, c->zc, c->zlo, zchunk, c->edge3.as<float>(),
-              c->face3.as<float>(), c->cube.as<float>(), want_radius ? c->radius.as<float>() : nullptr);
+    VC_TRY(measures_alloc(c, want_radius));
+    VC_TRY(measures_range(c, c->z0, c->z1, want_radius));
     VC_CUDA(c, cudaGetLastError());
     c->have_measures = true;
     return VC_OK;

@@ -547,6 +547,8 @@ static int bits_for(u64 maxval)
 int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key)
 {
     const int nlines = (c->nx + 1) * (c->ny + 1);
+    if (n > (int64_t)VC_MAX_SITE_ID + 1)
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "more than 2^26 sites: ids no longer fit the transform's packed stack entries");
     c->nsites = n;
     c->lattice = true;
     c->cl_dim[0] = 0; // any cell list of a previous site set is stale
