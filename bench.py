@@ -299,8 +299,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()
         ctx.sites_import_global(ak.data_ptr(), ac.data_ptr(), ak.numel())
         state["nsites"] = ak.numel()
-        ctx.closest_grid(fetch=False)
-        ctx.cell_measures_grid(fetch=False)
+        ctx.closest_and_measures()
 
     def barrier():
         if dist is not None:

@@ -134,6 +134,15 @@ int vc_segment_max(vc_ctx* ctx, const int32_t* off, const int32_t* items, int64_
  * classify -> sites -> closest -> measures on the resident volume, all results left in device
  * memory (fetch with vc_download).  This is one "step" of bench.py. */
 int vc_run_dense(vc_ctx* ctx, int64_t* nsites);
+/* Stages 2 + 3 for the planes this ctx owns, once its sites are set (vc_extract_sites,
+ * vc_sites_import_global or vc_set_sites): the closest-site passes and the measures, pipelined
+ * over z chunks on the ctx's worker streams.  This is the second half of a multi-GPU step (the
+ * first half being classify + site detection + the site exchange).  Results stay on the device. */
+int vc_closest_and_measures(vc_ctx* ctx);
+/* Pipeline shape of vc_run_dense / vc_run_dense_host / vc_closest_and_measures: number of worker
+ * streams (1..16; 0 = everything on the main stream) and z planes per chunk (0 = automatic).
+ * Results do not depend on either.  Defaults: 8 workers, automatic (env VC_WORKERS / VC_ZCHUNK). */
+int vc_set_pipeline(vc_ctx* ctx, int workers, int zchunk);
 typedef enum vc_array
 {
     VC_ARR_INSIDE = 0,   /* uint8  [z][y][x]      */

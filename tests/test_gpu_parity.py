@@ -149,6 +149,96 @@ def test_slab_contexts_reproduce_whole_grid(ctx_factory):
         assert np.array_equal(pc, c[z0:z1]) and np.array_equal(pr, r[z0:z1])
 
 
+@pytest.mark.parametrize("workers,zchunk", [(0, 0), (1, 1), (3, 5), (8, 0), (16, 2), (2, 1000)])
+def test_pipeline_shape_does_not_change_results(ctx_factory, workers, zchunk):
+    """z-chunk pipeline over worker streams (halo plane recomputed per chunk) == the staged single-stream calls"""
+    vol = synth.assembly(44, count=14)
+    c = ctx_factory()
+    inside, sites = _run_all(c, vol)
+    ids, d2 = c.closest_grid()
+    e, f, cu, r = c.cell_measures_grid()
+    c.set_pipeline(workers, zchunk)
+    for _ in range(2):  # second pass: buffers reused, chunks race on the shared halo planes with equal values
+        assert c.run_dense() == len(sites)
+        assert np.array_equal(c.download(api.ARR_ID), ids) and np.array_equal(c.download(api.ARR_D2X4), d2)
+        assert np.array_equal(c.download(api.ARR_EDGE3), e) and np.array_equal(c.download(api.ARR_FACE3), f)
+        assert np.array_equal(c.download(api.ARR_CUBE), cu) and np.array_equal(c.download(api.ARR_RADIUS), r)
+
+
+def test_slab_contexts_pipelined_second_half(ctx_factory):
+    """the multi-GPU step as bench.py runs it: classify, detect, exchange, import, vc_closest_and_measures"""
+    vol = synth.twist(40)
+    nz, ny, nx = vol.shape
+    o_inside = ob.classify_grid(vol)
+    o_sites = ob.extract_sites(o_inside)
+    o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
+    oe, of, oc, orad = ob.cell_measures_grid(o_sites, o_ids, o_inside, nx, ny, nz)
+    cuts = [0, 9, 10, 31, 40]  # includes a one-plane slab
+    parts, recs = [], []
+    for k in range(len(cuts) - 1):
+        p = ctx_factory()
+        z0, z1 = cuts[k], cuts[k + 1]
+        p.set_grid(nx, ny, nz, z0, z1)
+        lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
+        p.upload_volume(vol[lo:hi], zlo=lo)
+        p.classify_grid(fetch=False)
+        n = p.sites_detect_local()
+        keys, corners = np.empty(n, np.uint64), np.empty(n, np.uint64)
+        p.sites_export_local(keys, corners)
+        parts.append(p)
+        recs.append((keys, corners))
+    keys = np.concatenate([k for k, _ in recs][::-1])  # any order of the records must do
+    corners = np.concatenate([c for _, c in recs][::-1])
+    for k, p in enumerate(parts):
+        z0, z1 = cuts[k], cuts[k + 1]
+        p.set_pipeline(4, 3)
+        p.sites_import_global(keys, corners, len(keys))
+        p.closest_and_measures()
+        assert np.array_equal(p.download(api.ARR_ID), o_ids[z0:z1]) and np.array_equal(p.download(api.ARR_D2X4), o_d2[z0:z1])
+        assert np.array_equal(p.download(api.ARR_EDGE3), oe[:, z0:z1]) and np.array_equal(p.download(api.ARR_FACE3), of[:, z0:z1])
+        assert np.array_equal(p.download(api.ARR_CUBE), oc[z0:z1]) and np.array_equal(p.download(api.ARR_RADIUS), orad[z0:z1])
+
+
+@pytest.mark.parametrize("fam,n", [("twist", 256), ("torus", 256), ("assembly", 200)])
+def test_full_size_properties(ctx_factory, fam, n):
+    """sizes the CPU oracle cannot finish: size-independent properties instead.
+    (1) d2x4 is exactly the distance to the reported site; (2) no site is closer at a sample of vertices
+    (brute force over all sites); (3) ties report the lowest id; (4) radius == sqrt(d2) in float32;
+    (5) measures are 0 wherever the anchor vertex is outside; (6) cube >= faces >= edges where valid."""
+    vol = synth.make(fam, n)
+    nz, ny, nx = vol.shape
+    c = ctx_factory()
+    c.set_grid(nx, ny, nz)
+    c.upload_volume(vol)
+    ns = c.run_dense()
+    sites = c.get_sites()
+    assert ns == len(sites) and ns > 0
+    inside = c.download(api.ARR_INSIDE)
+    assert np.array_equal(inside, (vol > 0).astype(np.uint8))
+    ids, d2 = c.download(api.ARR_ID), c.download(api.ARR_D2X4)
+    zz, yy, xx = np.meshgrid(np.arange(nz, dtype=np.float32), np.arange(ny, dtype=np.float32),
+                             np.arange(nx, dtype=np.float32), indexing="ij", sparse=True)
+    s = sites[ids]
+    chk = 4.0 * ((s[..., 0] - xx) ** 2 + (s[..., 1] - yy) ** 2 + (s[..., 2] - zz) ** 2)
+    assert np.array_equal(chk.astype(np.uint32), d2)                                     # (1)
+    rng = np.random.default_rng(n)
+    q = np.stack([rng.integers(0, nx, 600), rng.integers(0, ny, 600), rng.integers(0, nz, 600)], -1)
+    dd = 4.0 * ((sites[None, :, :].astype(np.float64) - q[:, None, :]) ** 2).sum(-1)
+    best = dd.min(1)
+    assert np.array_equal(best.astype(np.uint32), d2[q[:, 2], q[:, 1], q[:, 0]])           # (2)
+    first = np.array([np.flatnonzero(dd[i] == best[i])[0] for i in range(len(q))])
+    assert np.array_equal(first.astype(np.int32), ids[q[:, 2], q[:, 1], q[:, 0]])          # (3)
+    r = c.download(api.ARR_RADIUS)
+    assert np.array_equal(r, np.sqrt(d2.astype(np.float32) * np.float32(0.25)))            # (4)
+    e, f, cu = c.download(api.ARR_EDGE3), c.download(api.ARR_FACE3), c.download(api.ARR_CUBE)
+    out = inside == 0
+    assert not e[:, out].any() and not f[:, out].any() and not cu[out].any()               # (5)
+    v = cu > 0
+    assert (cu[v] >= f[:, v].max(0)).all() and (f.max(0)[v] >= 0).all()
+    vf = f[0] > 0
+    assert (f[0][vf] >= np.maximum(e[0], e[1])[vf]).all()                                   # (6)
+
+
 def test_set_sites_lattice_and_points(ctx):
     vol = synth.sphere(32)
     inside, sites = _run_all(ctx, vol)

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vc_classify_grid", "vc_classify_points", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_closest_grid",
     "vc_closest_points", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max",
-    "vc_run_dense", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
+    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
 
@@ -81,6 +81,8 @@ def load_library(path: str | None = None):
     lib.vc_vertex_radii.argtypes = [vp, vp, i64, vp, vp]
     lib.vc_segment_max.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp]
     lib.vc_run_dense.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_closest_and_measures.argtypes = [vp]
+    lib.vc_set_pipeline.argtypes = [vp, i32, i32]
     lib.vc_download.argtypes = [vp, i32, vp]
     lib.vc_device_ptr.argtypes = [vp, i32]
     lib.vc_device_ptr.restype = vp
@@ -276,6 +278,13 @@ class Context:
         n = C.c_int64()
         self._ck(self.lib.vc_run_dense(self.h, C.byref(n)))
         return n.value
+
+    def closest_and_measures(self):
+        """stages 2+3 for this ctx's planes (sites already set), pipelined over z chunks; results stay on the device"""
+        self._ck(self.lib.vc_closest_and_measures(self.h))
+
+    def set_pipeline(self, workers=8, zchunk=0):
+        self._ck(self.lib.vc_set_pipeline(self.h, workers, zchunk))
 
     def download(self, which) -> np.ndarray:
         s = self.slab_shape

@@ -118,8 +118,8 @@ extern "C"
             c->nworkers = atoi(e);
         if (const char* e = getenv("VC_ZCHUNK"))
             c->zchunk = atoi(e);
-        c->nworkers = c->nworkers < 1 ? 1 : (c->nworkers > VC_MAX_WORKERS ? VC_MAX_WORKERS : c->nworkers);
-        c->zchunk = c->zchunk < 1 ? 1 : c->zchunk;
+        c->nworkers = c->nworkers < 0 ? 0 : (c->nworkers > VC_MAX_WORKERS ? VC_MAX_WORKERS : c->nworkers);
+        c->zchunk = c->zchunk < 0 ? 0 : c->zchunk;
         bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < c->nworkers; ++i)
             ok = cudaStreamCreateWithFlags(&c->workers[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -483,6 +483,34 @@ extern "C"
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (nsites)
             *nsites = c->nsites;
+        return VC_OK;
+    }
+
+    int vc_closest_and_measures(vc_ctx* c)
+    {
+        if (!c)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        if (!c->have_sites)
+            return vc_fail(c, VC_ERR_STATE, "vc_closest_and_measures needs sites");
+        VC_TRY(st_closest_measures_pipelined(c, true));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        return VC_OK;
+    }
+
+    int vc_set_pipeline(vc_ctx* c, int workers, int zchunk)
+    {
+        if (!c || workers < 0 || workers > VC_MAX_WORKERS || zchunk < 0)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        for (int i = 0; i < workers; ++i)
+            if (!c->workers[i])
+            {
+                VC_CUDA(c, cudaStreamCreateWithFlags(&c->workers[i], cudaStreamNonBlocking));
+                VC_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+            }
+        c->nworkers = workers;
+        c->zchunk = zchunk;
         return VC_OK;
     }
 

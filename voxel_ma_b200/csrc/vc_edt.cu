@@ -281,14 +281,25 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         return st_measures(c, want_radius);
     }
     const int nplanes_all = c->zc - c->z0;
-    const int nchunks = (nplanes_all + c->zchunk - 1) / c->zchunk;
-    VC_TRY(edt_alloc(c, nchunks, c->zchunk + 1));
+    const int nw = c->profiling ? 0 : c->nworkers;
+    // chunk height: >= 32k lines per launch keeps a chunk's kernels efficient on their own (measured:
+    // 64 planes at 512^2, profiles/), VC_ZCHUNK overrides; one chunk when profiling
+    int zchunk = c->zchunk;
+    if (zchunk <= 0)
+    {
+        const int side = c->nx < c->ny ? c->nx : c->ny;
+        zchunk = (32768 + side - 1) / side;
+        zchunk = zchunk < 8 ? 8 : zchunk;
+    }
+    if (!nw || zchunk > nplanes_all)
+        zchunk = nplanes_all;
+    const int nchunks = (nplanes_all + zchunk - 1) / zchunk;
+    VC_TRY(edt_alloc(c, nchunks, zchunk + 1));
     if (!c->have_inside)
         return vc_fail(c, VC_ERR_STATE, "measures need vc_classify_grid");
     if (c->zhi < c->zc)
         return vc_fail(c, VC_ERR_STATE, "inside flags do not cover the halo plane");
     VC_TRY(measures_alloc(c, want_radius));
-    const int nw = c->profiling ? 0 : c->nworkers;
     if (nw)
     {
         VC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
@@ -296,12 +307,12 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
             VC_CUDA(c, cudaStreamWaitEvent(c->workers[i], c->ev_fork, 0));
     }
     int k = 0, status = VC_OK;
-    for (int zb = c->z0; zb < c->zc && status == VC_OK; zb += c->zchunk, ++k)
+    for (int zb = c->z0; zb < c->zc && status == VC_OK; zb += zchunk, ++k)
     {
-        const int ze = zb + c->zchunk < c->zc ? zb + c->zchunk : c->zc;
+        const int ze = zb + zchunk < c->zc ? zb + zchunk : c->zc;
         const int zh = ze < c->zc ? ze + 1 : ze; // transform range incl. the halo plane
         c->cur = nw ? c->workers[k % nw] : c->stream;
-        status = edt_range(c, zb, zh, k, c->zchunk + 1);
+        status = edt_range(c, zb, zh, k, zchunk + 1);
         const int me = ze < c->z1 ? ze : c->z1;
         if (status == VC_OK && zb < me)
             status = measures_range(c, zb, me, want_radius);

@@ -63,7 +63,7 @@ struct vc_ctx
     cudaStream_t cur = nullptr;            // stream VC_LAUNCH uses (== stream outside the pipeline)
     cudaStream_t workers[VC_MAX_WORKERS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[VC_MAX_WORKERS] = {};
-    int nworkers = 4, zchunk = 32;
+    int nworkers = 8, zchunk = 0; // zchunk 0 = automatic (vc_edt.cu)
     // grid: global size, owned vertex planes [z0,z1), closest planes [z0,zc), resident voxel planes [zlo,zhi)
     int nx = 0, ny = 0, nz = 0, z0 = 0, z1 = 0, zc = 0, zlo = 0, zhi = 0;
     bool have_grid = false, have_vol = false, have_inside = false, have_sites = false, have_closest = false,
