@@ -10,6 +10,11 @@ VARIANTS = {
     "pf2": ["-DVC_PF=2"],
     "nol2": ["-DVC_PF_L2=0"],
     "l2_96": ["-DVC_PF_L2=96"],
+    "occ40": ["-DXY_MINB_T=10", "-DXY_MINB_D=5"],
+    "occ48": ["-DXY_MINB_T=12", "-DXY_MINB_D=6"],
+    "occ24": ["-DXY_MINB_T=6", "-DXY_MINB_D=3"],
+    "ring16": ["-DSR_R=16", "-DXY_MINB_T=6"],
+    "ring4": ["-DSR_R=4"],
 }
 names = sys.argv[1:] or list(VARIANTS)
 for n in names:

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256)
 //                  asynchronous copy (cp.async, global -> shared, no register in between).  Each drain
 //                  commits exactly one copy group, so `wait_group SR_R-1` before reading a slot is
 //                  precisely "the copy issued SR_R drains ago has landed": a pop never waits for HBM.
+#ifndef SR_R
 #define SR_R 8
+#endif
 struct StackRing
 {
     u64* ring; // this thread's slot 0; slot i at ring[i * nthr]
@@ -135,8 +137,12 @@ struct StackRing
 #define XY_THREADS_T 128 // pass X: 4 warps x 4.25 KB of transpose tile
 #define XY_THREADS_D 256 // pass Y
 #define XY_TW 16         // targets per transposed store burst
+#ifndef XY_MINB_T
+#define XY_MINB_T 8 // resident blocks per SM the register allocation must allow (pass X / pass Y)
+#define XY_MINB_D 4
+#endif
 template <bool TRANSPOSE>
-__global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANSPOSE ? 8 : 4)
+__global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANSPOSE ? XY_MINB_T : XY_MINB_D)
     k_pass_xy(const u64* __restrict__ in, u64* __restrict__ G2, int* __restrict__ id_out, u32* __restrict__ d2_out,
               u64* __restrict__ stack, long nlines_total, int lines_per_plane, long in_plane_stride, long in_stride,
               int ncand, int ntgt)
