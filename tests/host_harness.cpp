@@ -91,16 +91,16 @@ extern "C"
             {
                 vc_u64* row = &G2[((size_t)vz * CY + cy) * nx];
                 vc_envelope_line(&G1[(size_t)vz * CX * CY + cy], (long)CY, CX, nx, stk,
-                                 [&](int t, vc_u64 v) { row[t] = v; });
+                                 [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; });
             }
         for (int vz = 0; vz < nzs; ++vz)
             for (int vx = 0; vx < nx; ++vx)
                 vc_envelope_line(&G2[(size_t)vz * CY * nx + vx], (long)nx, CY, ny, stk,
-                                 [&](int t, vc_u64 v)
+                                 [&](int t, uint32_t V, uint32_t id)
                                  {
                                      size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
-                                     id_out[o] = (int32_t)(uint32_t)v;
-                                     d2x4_out[o] = (uint32_t)(v >> 32);
+                                     id_out[o] = (int32_t)id;
+                                     d2x4_out[o] = V;
                                  });
     }
 
@@ -110,7 +110,7 @@ extern "C"
     {
         std::vector<vc_u64> stkv(ncand + 1);
         vc_stack_array stk{stkv.data()};
-        vc_envelope_line(in, 1L, ncand, ntgt, stk, [&](int t, vc_u64 v) { out[t] = v; });
+        vc_envelope_line(in, 1L, ncand, ntgt, stk, [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; });
     }
 
     // (key, corner) records of one z-slab, as vc_sites_detect_local reports them: corner planes

@@ -48,7 +48,7 @@ def test_envelope_line_random(n, dmax, density):
     rng = np.random.default_rng(n * 7 + dmax % 97)
     for rep in range(6):
         D = (rng.integers(0, dmax + 1, size=n).astype(np.uint64) // np.uint64(8)) * np.uint64(8) + np.uint64(1)
-        ids = rng.permutation(5_000_000)[:n].astype(np.uint64)
+        ids = rng.permutation(33_000_000)[:n].astype(np.uint64)
         H = (D << np.uint64(32)) | ids
         H[rng.random(n) > density] = np.uint64(0xFFFFFFFFFFFFFFFF)
         out = hc.envelope(H, n - 1)
@@ -68,7 +68,7 @@ def test_envelope_line_touching_parabolas(n, levels):
         base = int((2 * (max(t0, n - t0)) + 3) ** 2 + 64)
         # all parabolas through (t0, base): D_p = base - (2(t0-p)+1)^2, some pushed up by multiples of 8
         D = base - (2 * (t0 - p) + 1) ** 2 + 8 * rng.integers(0, levels, n)
-        ids = rng.permutation(60_000_000)[:n].astype(np.uint64)
+        ids = rng.permutation(33_000_000)[:n].astype(np.uint64)
         H = (D.astype(np.uint64) << np.uint64(32)) | ids
         H[rng.random(n) > 0.8] = np.uint64(0xFFFFFFFFFFFFFFFF)
         out = hc.envelope(H, n - 1)

@@ -56,7 +56,7 @@ VC_HD vc_u64 vc_eval(vc_u64 H, int p, int t)
 //
 // Memory behaviour is what bounds this scan (one thread per line, a dependent chain per step), so:
 //   - stack: the two upper entries live in registers; the rest is a per-line array of packed
-//     8-byte entries  D << 38 | id << 12 | p  (D < 2^26, id < 2^26, p < 2^12), CONTIGUOUS per line, so
+//     8-byte entries  g:27 | id:25 | p:12, CONTIGUOUS per line, so
 //     consecutive pops of a thread hit the same 32-byte sector.  (A thread-local CUDA array would
 //     interleave the 32 lanes of a warp word by word: lanes at different depths then touch 32
 //     different sectors per access.)
@@ -78,19 +78,21 @@ VC_HD vc_u64 vc_eval(vc_u64 H, int p, int t)
 #define VC_PREFETCH_L2(p) ((void)0)
 #endif
 
-#define VC_MAX_SITE_ID ((1 << 26) - 1) // ids must fit the packed stack entry
+#define VC_MAX_SITE_ID ((1 << 25) - 1) // ids must fit the packed stack entry
 
-struct vc_env_state
+// packed stack entry  g:27 | id:25 | p:12   (g = D + 4p^2 < 2^26 + 2^24, p <= 2048), laid out so that both
+// 32-bit halves are cheap to build:  hi = g << 5 | id >> 20,  lo = id << 12 | p
+VC_HD vc_u64 vc_ent_pack(int g, uint32_t id, int p)
 {
-    int q;              // index of the top entry; -1 = empty.  entry q = top, q-1 = sec, 0..q-2 in memory
-    vc_u64 Ht, Hs;      // words of top / second
-    int pt, ps;         // positions
-    int gt, gs;         // g = D + 4 p^2
-};
-
-VC_HD vc_u64 vc_ent_pack(vc_u64 H, int p)
+    uint32_t hi = ((uint32_t)g << 5) | (id >> 20), lo = (id << 12) | (uint32_t)p;
+    return ((vc_u64)hi << 32) | lo;
+}
+VC_HD void vc_ent_unpack(vc_u64 e, int& g, uint32_t& id, int& p)
 {
-    return ((H >> 32) << 38) | ((vc_u64)(uint32_t)H << 12) | (vc_u64)(uint32_t)p;
+    uint32_t hi = (uint32_t)(e >> 32), lo = (uint32_t)e;
+    p = (int)(lo & 0xFFFu);
+    id = (lo >> 12) | ((hi & 31u) << 20);
+    g = (int)(hi >> 5);
 }
 
 // Storage of the stack entries below the two in registers (depth d = 0 .. q-2).  The scan is written
@@ -109,52 +111,48 @@ struct vc_stack_array
     VC_HD vc_u64 drain(int d) { return a[d]; }
 };
 
-template <bool DRAIN, class Stack>
-VC_HD void vc_env_pop(vc_env_state& s, Stack& stk)
-{
-    --s.q;
-    s.Ht = s.Hs;
-    s.pt = s.ps;
-    s.gt = s.gs;
-    if (s.q >= 1)
-    {
-        vc_u64 e = DRAIN ? stk.drain(s.q - 1) : stk.load(s.q - 1);
-        s.ps = (int)(e & 0xFFFu);
-        s.Hs = ((e >> 38) << 32) | ((e >> 12) & 0x3FFFFFFu);
-        s.gs = (int)(e >> 38) + 4 * s.ps * s.ps;
-    }
-}
-
-template <class Stack>
-VC_HD void vc_env_push(vc_env_state& s, vc_u64 H, int j, Stack& stk)
-{
-    if (H == VC_INF)
-        return;
-    const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
-    while (s.q >= 1 &&
-           (long long)(s.gt - s.gs) * (long long)(j - s.pt) > (long long)(g - s.gt) * (long long)(s.pt - s.ps))
-        vc_env_pop<false>(s, stk); // top strictly hidden by (second, new)
-    if (s.q >= 1)
-        stk.store(s.q - 1, vc_ent_pack(s.Hs, s.ps));
-    if (s.q >= 0)
-    {
-        s.Hs = s.Ht;
-        s.ps = s.pt;
-        s.gs = s.gt;
-    }
-    ++s.q;
-    s.Ht = H;
-    s.pt = j;
-    s.gt = g;
-}
-
+// emit(t, V, id): the winner at target t has 4*d^2-so-far V and site id `id` (both 0xFFFFFFFF: no candidate)
 template <class Stack, class Emit>
 VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt, Stack& stk, Emit emit)
 {
-    vc_env_state s;
-    s.q = -1;
-    s.Ht = s.Hs = 0;
-    s.pt = s.ps = s.gt = s.gs = 0;
+    // two upper entries in registers: top (gt, pt, idt) and second (gs, ps, ids); a = gt - gs, b = pt - ps
+    int q = -1, gt = 0, pt = 0, gs = 0, ps = 0, a = 0, b = 1;
+    uint32_t idt = 0, ids = 0;
+    auto push = [&](vc_u64 H, int j)
+    {
+        const uint32_t D = (uint32_t)(H >> 32);
+        if (D == 0xFFFFFFFFu)
+            return; // VC_INF: this position has no candidate
+        const int g = (int)D + 4 * j * j;
+        // top strictly hidden by (second, new):  (gt-gs)(j-pt) > (g-gt)(pt-ps)
+        while (q >= 1 && (long long)a * (long long)(j - pt) > (long long)(g - gt) * (long long)b)
+        {
+            --q;
+            gt = gs;
+            pt = ps;
+            idt = ids;
+            if (q >= 1)
+            {
+                vc_ent_unpack(stk.load(q - 1), gs, ids, ps);
+                a = gt - gs;
+                b = pt - ps;
+            }
+        }
+        if (q >= 1)
+            stk.store(q - 1, vc_ent_pack(gs, ids, ps));
+        if (q >= 0)
+        {
+            a = g - gt;
+            b = j - pt;
+            gs = gt;
+            ps = pt;
+            ids = idt;
+        }
+        gt = g;
+        pt = j;
+        idt = (uint32_t)H;
+        ++q;
+    };
     vc_u64 bankA[VC_PF], bankB[VC_PF];
 #define VC_FETCH(bank, j0)                                                                         \
     _Pragma("unroll") for (int k = 0; k < VC_PF; ++k)                                              \
@@ -163,8 +161,7 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
         if (VC_PF_L2 > 0 && (j0) + k + VC_PF_L2 < ncand)                                           \
             VC_PREFETCH_L2(in + (long)((j0) + k + VC_PF_L2) * stride);                             \
     }
-#define VC_CONSUME(bank, j0)                                                                       \
-    _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) vc_env_push(s, bank[k], (j0) + k, stk);
+#define VC_CONSUME(bank, j0) _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) push(bank[k], (j0) + k);
     if (VC_PF_L2 > 0)
         for (int j = 0; j < VC_PF_L2 && j < ncand; ++j)
             VC_PREFETCH_L2(in + (long)j * stride);
@@ -178,26 +175,47 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
     }
 #undef VC_FETCH
 #undef VC_CONSUME
-    // one uniform backward loop (a line without candidates emits VC_INF) so that a warp whose
-    // lanes each own a line stays convergent at the emit() call and may synchronise inside it
-    const bool empty = s.q < 0;
-    stk.begin_drain(s.q - 2);
+    // Backward scan.  With x = 2t+1 a candidate's value is V(t) = g + x (x - 4p); stepping t -> t-1
+    // changes it by -m with m = 4 (x - 2p - 1), and m itself by -8: two additions per entry per target.
+    // One uniform loop over t (a line without candidates emits all-ones) so that a warp whose lanes each
+    // own a line stays convergent at the emit() call and may synchronise inside it.
+    stk.begin_drain(q - 2);
+    const bool empty = q < 0;
+    int x = 2 * (ntgt - 1) + 1;
+    uint32_t Vt = (uint32_t)(gt + x * (x - 4 * pt)), Vs = (uint32_t)(gs + x * (x - 4 * ps));
+    int mt = 4 * (x - 2 * pt - 1), ms = 4 * (x - 2 * ps - 1);
     for (int t = ntgt - 1; t >= 0; --t)
     {
-        vc_u64 best = VC_INF;
+        uint32_t bV = 0xFFFFFFFFu, bid = 0xFFFFFFFFu;
         if (!empty)
         {
-            best = vc_eval(s.Ht, s.pt, t);
-            while (s.q > 0)
-            {
-                const vc_u64 vs = vc_eval(s.Hs, s.ps, t);
-                if ((uint32_t)(vs >> 32) > (uint32_t)(best >> 32))
-                    break;
-                best = vs < best ? vs : best;
-                vc_env_pop<true>(s, stk);
+            bV = Vt;
+            bid = idt;
+            while (q > 0 && Vs <= bV)
+            { // the entry below is at least as close: the top never wins again left of here
+                if (Vs < bV || ids < bid)
+                {
+                    bV = Vs;
+                    bid = ids;
+                }
+                --q;
+                Vt = Vs;
+                mt = ms;
+                idt = ids;
+                if (q >= 1)
+                {
+                    vc_ent_unpack(stk.drain(q - 1), gs, ids, ps);
+                    Vs = (uint32_t)(gs + x * (x - 4 * ps));
+                    ms = 4 * (x - 2 * ps - 1);
+                }
             }
         }
-        emit(t, best);
+        emit(t, bV, bid);
+        Vt -= (uint32_t)mt;
+        mt -= 8;
+        Vs -= (uint32_t)ms;
+        ms -= 8;
+        x -= 2;
     }
 }
 

@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANS
     {
         const int rsub = lane / XY_TW, col = lane % XY_TW; // a store instruction covers 32/XY_TW rows
         vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stk,
-                         [&](int t, u64 v)
+                         [&](int t, u32 V, u32 id)
                          {
-                             tile[warp][lane][t % XY_TW] = v;
+                             tile[warp][lane][t % XY_TW] = ((u64)V << 32) | id;
                              if ((t % XY_TW) == 0)
                              {
                                  __syncwarp();
@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANS
         int* pid = id_out + last;
         u32* pd2 = d2_out + last;
         vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stk,
-                         [&](int t, u64 v)
+                         [&](int t, u32 V, u32 id)
                          { // targets arrive as ntgt-1 .. 0
                              if (valid)
                              {
-                                 __stcs(pid, (int)(u32)v);
-                                 __stcs(pd2, (u32)(v >> 32));
+                                 __stcs(pid, (int)id);
+                                 __stcs(pd2, V);
                              }
                              pid -= lines_per_plane;
                              pd2 -= lines_per_plane;
