@@ -73,6 +73,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DROPIN_CLI = os.path.join(HERE, "host", "_build", "main_voroUtility_gpu")
+
+
+def build_dropin_cli(reference_tree: str = "/root/reference"):
+    """The reference CLI linked against host/dropin/*.cpp + libvoxcore_gpu.so (host/Makefile.dropin).
+    Needs the reference tree and its objects (oracle/_ref/obj, built by oracle/Makefile.ref): possible
+    in the build container only; the binary then travels with the snapshot.  Returns its path or None."""
+    root = os.path.dirname(HERE)
+    if not (os.path.isdir(reference_tree) and os.path.isdir(os.path.join(root, "oracle", "_ref", "obj"))):
+        return DROPIN_CLI if os.path.exists(DROPIN_CLI) else None
+    r = subprocess.run(["make", "-f", os.path.join("voxel_ma_b200", "host", "Makefile.dropin"), f"REF={reference_tree}"],
+                       cwd=root, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"drop-in CLI build failed:\n{r.stdout}\n{r.stderr}")
+    return DROPIN_CLI
+
+
 def build_variant(name: str, defines) -> str:
     """Development aid: the same sources with extra -D flags -> lib/variants/libvoxcore_gpu_<name>.so"""
     vdir = os.path.join(LIBDIR, "variants", name)

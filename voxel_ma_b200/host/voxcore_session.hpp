@@ -1,0 +1,181 @@
+// voxcore_session.hpp -- C++ host side above the C ABI (include/voxcore_gpu.h).
+//
+// The reference (danielyan86129/voxel_ma) is a single-threaded C++ program whose hot functions
+// receive a shared_ptr<Volume3DScalar> and std::vector out-parameters.  A drop-in
+// for those functions needs somewhere to keep the GPU context and to remember which volume and
+// which sample set are resident between two calls that, in the reference, share nothing but their
+// arguments.  That is this class: one process-wide session = one vc_ctx on one B200.
+//
+// Error convention follows the reference (SURVEY 8b "Errors"): message to std::cout, a false / error
+// code return, never an exception.  There is no CPU fallback: when the CUDA library cannot create a
+// context the session reports it and every drop-in function fails.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "voxcore_gpu.h"
+
+namespace vcgpu
+{
+// 64-bit FNV-1a over a byte range: identity of a resident sample set / volume payload
+inline uint64_t fingerprint(const void* p, size_t n, uint64_t h = 1469598103934665603ull)
+{
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i)
+        h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
+class Session
+{
+public:
+    static Session& get()
+    {
+        static Session s;
+        return s;
+    }
+    bool ok() const { return m_ctx != nullptr; }
+    vc_ctx* ctx() { return m_ctx; }
+    // reports a failed ABI call the way the reference reports errors; returns false on failure
+    bool check(int status, const char* what)
+    {
+        if (status == VC_OK)
+            return true;
+        std::cout << "Error: GPU front end (" << what << "): " << (m_ctx ? vc_last_error(m_ctx) : "no context") << std::endl;
+        return false;
+    }
+
+    // Makes a dense volume the resident, classified volume.  `owner` identifies the volume object
+    // (the Volume3DScalar the reference passes around); zfast is Tao's in-memory order
+    // double[x*ny*nz + y*nz + z] (3rdparty/isosurface_tao/volume.h:217-224).
+    bool set_volume(const void* owner, const double* zfast, int nx, int ny, int nz)
+    {
+        if (!ok())
+            return false;
+        const uint64_t fp = fingerprint(zfast, sizeof(double) * (size_t)nx * ny * nz);
+        if (owner == m_vol_owner && fp == m_vol_fp && nx == m_n[0] && ny == m_n[1] && nz == m_n[2])
+            return true;
+        m_vol_owner = nullptr;
+        m_sites_fp = 0;
+        if (!check(vc_set_grid(m_ctx, nx, ny, nz, 0, nz), "vc_set_grid") ||
+            !check(vc_volume_upload_f64_zfast(m_ctx, zfast), "vc_volume_upload_f64_zfast") ||
+            !check(vc_classify_grid(m_ctx, nullptr), "vc_classify_grid"))
+            return false;
+        m_vol_owner = owner;
+        m_vol_fp = fp;
+        m_n[0] = nx, m_n[1] = ny, m_n[2] = nz;
+        return true;
+    }
+    bool volume_is(const void* owner) const { return owner && owner == m_vol_owner; }
+
+    // Sites of the resident volume in the reference's numbering; remembers them as the resident set.
+    bool extract_sites(std::vector<float>& xyz)
+    {
+        int64_t n = 0;
+        if (!check(vc_extract_sites(m_ctx, &n), "vc_extract_sites"))
+            return false;
+        xyz.resize((size_t)n * 3);
+        if (n && !check(vc_get_sites(m_ctx, xyz.data()), "vc_get_sites"))
+            return false;
+        m_sites_fp = fingerprint(xyz.data(), xyz.size() * sizeof(float)) | 1;
+        return true;
+    }
+    // Makes `xyz` (n float triples) the resident sample set unless it already is.
+    bool set_sites(const float* xyz, int64_t n)
+    {
+        if (!ok())
+            return false;
+        const uint64_t fp = fingerprint(xyz, (size_t)n * 3 * sizeof(float)) | 1;
+        if (fp == m_sites_fp)
+            return true;
+        if (!m_n[0])
+        { // no volume yet (a Voronoi diagram loaded from files): a grid that bounds the samples
+            float hi[3] = {1, 1, 1};
+            for (int64_t i = 0; i < 3 * n; ++i)
+                if (xyz[i] > hi[i % 3])
+                    hi[i % 3] = xyz[i];
+            for (int d = 0; d < 3; ++d)
+                m_n[d] = (int)hi[d] + 2;
+            if (!check(vc_set_grid(m_ctx, m_n[0], m_n[1], m_n[2], 0, m_n[2]), "vc_set_grid"))
+                return false;
+        }
+        if (!check(vc_set_sites(m_ctx, xyz, n), "vc_set_sites"))
+            return false;
+        m_sites_fp = fp;
+        return true;
+    }
+
+    // ---- batched inside/outside tags consumed one by one ------------------------------------
+    // The reference asks tagVert() once per Voronoi vertex from inside a loader loop
+    // (src/voroinfo.cpp:128-139).  The drop-in classifies the whole vertex list in one
+    // vc_classify_points call before the loop starts and hands the answers out in order.
+    bool prefetch_tags(const std::vector<float>& xyz)
+    {
+        m_tag_pts = xyz;
+        m_tags.assign(xyz.size() / 3, 0);
+        m_tag_cursor = 0;
+        if (m_tags.empty())
+            return true;
+        return check(vc_classify_points(m_ctx, m_tag_pts.data(), (int64_t)m_tags.size(), nullptr, m_tags.data()),
+                     "vc_classify_points");
+    }
+    void drop_tags()
+    {
+        m_tags.clear();
+        m_tag_pts.clear();
+        m_tag_cursor = 0;
+    }
+    // tag of point p: the prefetched answer when p is the next prefetched point, else one query
+    bool tag(const float p[3], bool& inside)
+    {
+        if (m_tag_cursor < m_tags.size() && std::memcmp(p, &m_tag_pts[3 * m_tag_cursor], 12) == 0)
+        {
+            inside = m_tags[m_tag_cursor++] != 0;
+            ++m_tag_hits;
+            return true;
+        }
+        uint8_t f = 0;
+        if (!check(vc_classify_points(m_ctx, p, 1, nullptr, &f), "vc_classify_points"))
+            return false;
+        inside = f != 0;
+        ++m_tag_misses;
+        return true;
+    }
+    size_t tag_hits() const { return m_tag_hits; }
+    size_t tag_misses() const { return m_tag_misses; }
+
+private:
+    Session()
+    {
+        const char* dev = std::getenv("VC_DEVICE");
+        vc_ctx* c = nullptr;
+        int st = vc_ctx_create(dev ? std::atoi(dev) : 0, &c);
+        if (st != VC_OK)
+        {
+            std::cout << "Error: GPU front end unavailable (vc_ctx_create = " << st
+                      << "); this build has no CPU path for classification / closest-site / measures." << std::endl;
+            m_ctx = nullptr;
+        }
+        else
+            m_ctx = c;
+    }
+    ~Session()
+    {
+        if (m_ctx)
+            vc_ctx_destroy(m_ctx);
+    }
+    Session(const Session&) = delete;
+    Session& operator=(const Session&) = delete;
+
+    vc_ctx* m_ctx = nullptr;
+    const void* m_vol_owner = nullptr;
+    uint64_t m_vol_fp = 0, m_sites_fp = 0;
+    int m_n[3] = {0, 0, 0};
+    std::vector<float> m_tag_pts;
+    std::vector<uint8_t> m_tags;
+    size_t m_tag_cursor = 0, m_tag_hits = 0, m_tag_misses = 0;
+};
+} // namespace vcgpu
