@@ -79,6 +79,18 @@ int vc_classify_grid(vc_ctx* ctx, uint8_t* inside_out);
  * ctx must hold the whole grid.  xyz, out: host. */
 int vc_classify_points(vc_ctx* ctx, const float* xyz, int64_t n, const double* M, uint8_t* out);
 
+/* ---- stage 1': inside / outside straight from a closed triangle mesh ------------------------------
+ * New surface (SURVEY section 8a "K1'", 8f): the reference only ever sees a voxelised volume.  Parity
+ * rule: voxel centre (i,j,k) is inside iff its +x ray crosses the mesh an odd number of times.
+ * verts = nv x 3 float32 in model space, tris = nt x 3 uint32, M = model -> voxel transform (double
+ * 4x4, column-major, NULL = identity) applied like VoroInfo::tagVert's (XForm.h:479-489); transformed
+ * vertices are snapped to 1/256 voxel and every decision is exact integer arithmetic, so the flags
+ * are reproducible bit for bit (rules: voxel_ma_b200/csrc/vc_mesh_core.h).  Vertices must lie within
+ * [-1024, 3072) voxels.  The flags replace an uploaded volume: the sites / closest / measures stages
+ * run on them unchanged.  Needs vc_set_grid.  verts, tris: host or device; inside_out nullable. */
+int vc_classify_mesh(vc_ctx* ctx, const float* verts, int64_t nv, const uint32_t* tris, int64_t nt, const double* M,
+                     uint8_t* inside_out);
+
 /* ---- stage 1'': boundary samples ("sites") ----------------------------------------------------
  * a3: Surfacer::extractBoundaryVts (src/surfacing.cpp:223-321): the unique corners of all voxel
  * faces that separate a 0-voxel from a 1-voxel, numbered in the reference's first-encounter order

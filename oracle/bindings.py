@@ -75,6 +75,8 @@ def oracle():
         lib.orc_segment_max.argtypes = [_i32p, _i32p, C.c_int64, _f32p, C.c_void_p, _f32p]
         lib.orc_cell_measures_grid.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                _f32p, _f32p, _f32p, C.c_void_p]
+        lib.orc_classify_mesh.argtypes = [_f32p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.orc_classify_mesh.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -137,6 +139,18 @@ def classify_points(inside: np.ndarray, xyz: np.ndarray, M=None) -> np.ndarray:
     oracle().orc_classify_points(np.ascontiguousarray(inside, np.uint8), *_dims(inside), xyz, len(xyz),
                                  None if m is None else m.ctypes.data, out)
     return out
+
+
+def classify_mesh(verts, tris, nx, ny, nz, M=None):
+    """1' (parity unpinned): even-odd classification of the grid from a closed triangle mesh.
+    Returns (rc, inside[z][y][x])."""
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    tris = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+    m = None if M is None else np.ascontiguousarray(M, np.float64)
+    out = np.empty((nz, ny, nx), np.uint8)
+    rc = oracle().orc_classify_mesh(verts, len(verts), tris.ctypes.data, len(tris), None if m is None else m.ctypes.data,
+                                    nx, ny, nz, out)
+    return rc, out
 
 
 def extract_sites(inside: np.ndarray) -> np.ndarray:

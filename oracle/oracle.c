@@ -338,3 +338,102 @@ void orc_cell_measures_grid(const float* sites_xyz, const int32_t* id, const uin
 #undef L
 #undef MAX2
 }
+
+/* ---- 1': parity classification of the grid from a closed triangle mesh --------------------------
+ * PARITY UNPINNED: the reference has no mesh voxeliser (stage 1'), so there is
+ * nothing of the reference to pin this against.  It is pinned instead (tests/test_mesh_classify.py)
+ * against analytic solids (sphere / torus implicit functions away from the surface) and against the
+ * brute-force even-odd count below, which is written triangle-major with plain loops and shares no
+ * code with the CUDA kernels.
+ *
+ * Rule (the product states the same in voxel_ma_b200/csrc/vc_mesh_core.h):
+ *   vertices: q = M*p as in orc_classify_points (double 4x4, homogeneous divide, cast to float),
+ *             snapped to 1/256 voxel, Q = floor(256 q + 0.5);
+ *   voxel centre (i,j,k) is inside iff an odd number of triangles T satisfy
+ *       (a) (256 j, 256 k) lies in T's (y,z) projection -- a point on an edge U->V of the
+ *           counter-clockwise projection counts iff U > V in (y, then z) order, and
+ *       (b) 256 i < x_T(j,k), the abscissa of T's plane over that point (an exact rational). */
+static long long orc_orient2(long long uy, long long uz, long long vy, long long vz, long long py, long long pz)
+{
+    return (vy - uy) * (pz - uz) - (vz - uz) * (py - uy);
+}
+static int orc_edge_owns(long long w, long long uy, long long uz, long long vy, long long vz)
+{
+    if (w != 0)
+        return w > 0;
+    return uy > vy || (uy == vy && uz > vz);
+}
+/* returns 0 on success, 1 when a vertex is out of the supported range [-1024, 3072) voxels, 2 on a bad index */
+int orc_classify_mesh(const float* verts, int64_t nv, const uint32_t* tris, int64_t nt, const double* M, int nx, int ny,
+                      int nz, uint8_t* inside)
+{
+    static const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const double* xf = M ? M : I;
+    long long* Q = (long long*)malloc(sizeof(long long) * 3 * (size_t)(nv > 0 ? nv : 1));
+    int rc = 0;
+    for (int64_t i = 0; i < nv; ++i)
+    {
+        double v0 = verts[3 * i], v1 = verts[3 * i + 1], v2 = verts[3 * i + 2];
+        double h = 1 / (xf[3] * v0 + xf[7] * v1 + xf[11] * v2 + xf[15]);
+        float q[3];
+        q[0] = (float)(h * (xf[0] * v0 + xf[4] * v1 + xf[8] * v2 + xf[12]));
+        q[1] = (float)(h * (xf[1] * v0 + xf[5] * v1 + xf[9] * v2 + xf[13]));
+        q[2] = (float)(h * (xf[2] * v0 + xf[6] * v1 + xf[10] * v2 + xf[14]));
+        for (int d = 0; d < 3; ++d)
+        {
+            double s = floor((double)q[d] * 256.0 + 0.5);
+            if (!(s >= -262144.0 && s <= 786431.0))
+                rc = 1;
+            else
+                Q[3 * i + d] = (long long)s;
+        }
+    }
+    memset(inside, 0, (size_t)nx * ny * nz);
+    for (int64_t t = 0; t < nt && rc == 0; ++t)
+    {
+        if (tris[3 * t] >= nv || tris[3 * t + 1] >= nv || tris[3 * t + 2] >= nv)
+        {
+            rc = 2;
+            break;
+        }
+        const long long* A = Q + 3 * (size_t)tris[3 * t];
+        const long long* B = Q + 3 * (size_t)tris[3 * t + 1];
+        const long long* C = Q + 3 * (size_t)tris[3 * t + 2];
+        long long area = orc_orient2(A[1], A[2], B[1], B[2], C[1], C[2]);
+        if (area == 0)
+            continue; /* seen edge-on from +x: never crossed */
+        if (area < 0)
+        {
+            const long long* s = B;
+            B = C;
+            C = s;
+            area = -area;
+        }
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j)
+            {
+                const long long py = 256LL * j, pz = 256LL * k;
+                /* cheap reject outside the box of the projection */
+                if ((py < A[1] && py < B[1] && py < C[1]) || (py > A[1] && py > B[1] && py > C[1]) ||
+                    (pz < A[2] && pz < B[2] && pz < C[2]) || (pz > A[2] && pz > B[2] && pz > C[2]))
+                    continue;
+                long long wa = orc_orient2(B[1], B[2], C[1], C[2], py, pz);
+                long long wb = orc_orient2(C[1], C[2], A[1], A[2], py, pz);
+                long long wc = orc_orient2(A[1], A[2], B[1], B[2], py, pz);
+                if (!orc_edge_owns(wa, B[1], B[2], C[1], C[2]) || !orc_edge_owns(wb, C[1], C[2], A[1], A[2]) ||
+                    !orc_edge_owns(wc, A[1], A[2], B[1], B[2]))
+                    continue;
+                /* x_T = (wa*Ax + wb*Bx + wc*Cx) / area;  256 i < x_T  <=>  256 i area < that sum (128-bit safe) */
+                __int128 sum = (__int128)wa * A[0] + (__int128)wb * B[0] + (__int128)wc * C[0];
+                for (int i = 0; i < nx; ++i)
+                {
+                    if ((__int128)256 * i * area < sum)
+                        inside[IDX(i, j, k)] ^= 1;
+                    else
+                        break;
+                }
+            }
+    }
+    free(Q);
+    return rc;
+}

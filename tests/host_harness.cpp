@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../voxel_ma_b200/csrc/vc_core.h"
+#include "../voxel_ma_b200/csrc/vc_mesh_core.h"
 
 extern "C"
 {
@@ -145,5 +146,45 @@ extern "C"
                     ++n;
                 }
         return n;
+    }
+    // Mesh parity classification with the kernels' own rules (vc_mesh_core.h) and data flow: snapped
+    // vertices -> one toggle bit per (triangle, covered column) in rows of nx+1 bits -> exclusive suffix
+    // parity per row.  q = already transformed float coordinates (identity M).  Returns 0 / 1 (range).
+    int hh_classify_mesh(const float* q, int64_t nv, const uint32_t* tris, int64_t nt, int nx, int ny, int nz, uint8_t* inside)
+    {
+        std::vector<int> Q((size_t)nv * 3);
+        for (int64_t i = 0; i < 3 * nv; ++i)
+            if (!vc_mesh_snap(q[i], &Q[i]))
+                return 1;
+        const int wr = nx / 32 + 1;
+        std::vector<uint32_t> tog((size_t)ny * nz * wr, 0u);
+        for (int64_t t = 0; t < nt; ++t)
+        {
+            int a[3], b[3], c[3];
+            for (int d = 0; d < 3; ++d)
+                a[d] = Q[3 * tris[3 * t] + d], b[d] = Q[3 * tris[3 * t + 1] + d], c[d] = Q[3 * tris[3 * t + 2] + d];
+            if (!vc_mesh_orient_ccw(&a[0], &a[1], &a[2], &b[0], &b[1], &b[2], &c[0], &c[1], &c[2]))
+                continue;
+            int j0, j1, k0, k1;
+            vc_mesh_columns(a[1], a[2], b[1], b[2], c[1], c[2], ny, 0, nz, &j0, &j1, &k0, &k1);
+            for (int k = k0; k <= k1; ++k)
+                for (int j = j0; j <= j1; ++j)
+                {
+                    int T;
+                    if (vc_mesh_crossing(a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2], j, k, nx, &T) && T > 0)
+                        tog[((size_t)k * ny + j) * wr + (T >> 5)] ^= 1u << (T & 31);
+                }
+        }
+        for (size_t row = 0; row < (size_t)ny * nz; ++row)
+        {
+            int par = 0;
+            for (int x = nx; x >= 0; --x)
+            { // inside(x) = parity of the toggles strictly above x
+                if (x < nx)
+                    inside[row * nx + x] = (uint8_t)par;
+                par ^= (tog[row * wr + (x >> 5)] >> (x & 31)) & 1u;
+            }
+        }
+        return 0;
     }
 }

@@ -14,8 +14,8 @@ def lib():
     global _lib
     if _lib is None:
         src = os.path.join(HERE, "host_harness.cpp")
-        hdr = os.path.join(HERE, "..", "voxel_ma_b200", "csrc", "vc_core.h")
-        if (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        hdrs = [os.path.join(HERE, "..", "voxel_ma_b200", "csrc", h) for h in ("vc_core.h", "vc_mesh_core.h")]
+        if (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in [src, *hdrs]):
             os.makedirs(os.path.dirname(SO), exist_ok=True)
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
         L = C.CDLL(SO)
@@ -63,3 +63,11 @@ def site_records(inside_planes, nx, ny, nz, zlo, czb, cze):
     c = np.empty(n, np.uint64)
     lib().hh_site_records(_p(ins), nx, ny, nz, zlo, zhi, czb, cze, _p(k), _p(c), C.c_int64(n))
     return k, c
+
+
+def classify_mesh(verts, tris, nx, ny, nz):
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+    out = np.empty((nz, ny, nx), np.uint8)
+    rc = lib().hh_classify_mesh(_p(v), C.c_int64(len(v)), _p(t), C.c_int64(len(t)), nx, ny, nz, _p(out))
+    return rc, out

@@ -22,7 +22,7 @@ ARR_INSIDE, ARR_ID, ARR_D2X4, ARR_EDGE3, ARR_FACE3, ARR_CUBE, ARR_RADIUS = range
 SYMBOLS = [
     "vc_abi_version", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
     "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_f64_zfast",
-    "vc_classify_grid", "vc_classify_points", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
+    "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_closest_grid",
     "vc_closest_points", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
@@ -66,6 +66,7 @@ def load_library(path: str | None = None):
     lib.vc_volume_upload_f64_zfast.argtypes = [vp, vp]
     lib.vc_classify_grid.argtypes = [vp, vp]
     lib.vc_classify_points.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_classify_mesh.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     lib.vc_extract_sites.argtypes = [vp, C.POINTER(i64)]
     lib.vc_get_sites.argtypes = [vp, vp]
     lib.vc_set_sites.argtypes = [vp, vp, i64]
@@ -189,6 +190,15 @@ class Context:
     def classify_grid(self, fetch=True):
         out = np.empty(self.slab_shape, np.uint8) if fetch else None
         self._ck(self.lib.vc_classify_grid(self.h, _ptr(out)))
+        return out
+
+    def classify_mesh(self, verts, tris, M=None, fetch=True):
+        """Stage 1': parity classification of the grid from a closed triangle mesh (vc_classify_mesh)."""
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+        m = None if M is None else np.ascontiguousarray(M, np.float64)
+        out = np.empty(self.slab_shape, np.uint8) if fetch else None
+        self._ck(self.lib.vc_classify_mesh(self.h, _ptr(v), len(v), _ptr(t), len(t), _ptr(m), _ptr(out)))
         return out
 
     def classify_points(self, xyz, M=None):

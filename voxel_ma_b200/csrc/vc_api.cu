@@ -273,6 +273,18 @@ extern "C"
         return VC_OK;
     }
 
+    int vc_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* tris, int64_t nt, const double* M,
+                         uint8_t* inside_out)
+    {
+        if (!c || nv < 0 || nt < 0 || (nv > 0 && !verts) || (nt > 0 && !tris))
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        VC_TRY(st_classify_mesh(c, verts, nv, tris, nt, M));
+        VC_TRY(copy_out(c, inside_out, c->inside.as<u8>() + owned_offset(c, c->zlo), owned_count(c)));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        return VC_OK;
+    }
+
     int vc_classify_points(vc_ctx* c, const float* xyz, int64_t n, const double* M, uint8_t* out)
     {
         if (!c || n < 0 || (n > 0 && (!xyz || !out)))
@@ -476,7 +488,8 @@ extern "C"
         VC_CUDA(c, cudaSetDevice(c->device));
         if (c->z0 != 0 || c->z1 != c->nz)
             return vc_fail(c, VC_ERR_STATE, "vc_run_dense: slab contexts run the stages one by one around the site exchange");
-        VC_TRY(st_classify(c));
+        if (c->have_vol || !c->have_inside) // flags from vc_classify_mesh / the f64 upload stand in for a volume
+            VC_TRY(st_classify(c));
         VC_TRY(st_detect_sites(c));
         VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
         VC_TRY(st_closest_measures_pipelined(c, true));

@@ -162,6 +162,7 @@ int st_vertex_radii(vc_ctx* c, const float* v, int64_t nv, const int32_t* site_o
 int st_segment_max(vc_ctx* c, const int32_t* off, const int32_t* items, int64_t n, const float* value,
                    int64_t nvalue, const uint8_t* valid, float* out);
 int st_upload_f64_zfast(vc_ctx* c, const double* vol);
+int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* tris, int64_t nt, const double* M);
 // general sites
 int st_build_cell_list(vc_ctx* c, const float* xyz_host, int64_t n);
 int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double* d2);

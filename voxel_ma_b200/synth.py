@@ -178,3 +178,87 @@ def read_mrc(path: str) -> np.ndarray:
         nx, ny, nz, mode = struct.unpack_from("<4i", hdr, 0)
         assert mode == 2, "only MRC mode 2 (float32) is produced by this package"
         return np.frombuffer(f.read(), dtype=np.float32, count=nx * ny * nz).reshape(nz, ny, nx).copy()
+
+
+# ---- closed triangle meshes (inputs of vc_classify_mesh, stage 1') ----------------------------------
+def _param_mesh(fn, nu: int, nv: int, wrap_v: bool):
+    """Triangles of a (u, v) parameter grid; u always wraps, v wraps for a torus.  Vertex (a, b) =
+    fn(2 pi a / nu, b / nv')."""
+    a = np.arange(nu)
+    b = np.arange(nv if wrap_v else nv + 1)
+    U, V = np.meshgrid(a, b, indexing="ij")
+    verts = fn(U.ravel(), V.ravel()).astype(np.float32)
+    nb = len(b)
+    idx = lambda i, j: (i % nu) * nb + (j % nb if wrap_v else j)  # noqa: E731
+    tris = []
+    for i in range(nu):
+        for j in range(nv):
+            p00, p10, p01, p11 = idx(i, j), idx(i + 1, j), idx(i, j + 1), idx(i + 1, j + 1)
+            tris.append((p00, p10, p11))
+            tris.append((p00, p11, p01))
+    return verts, np.asarray(tris, np.uint32)
+
+
+def sphere_mesh(n: int, nu: int = 96, nv: int = 48, radius: float | None = None, center=None):
+    """Closed UV sphere in voxel space (poles are rings of coincident vertices: degenerate triangles
+    there exercise the zero-area rule).  Default radius 0.35 n, centred off-lattice."""
+    r = 0.35 * n if radius is None else radius
+    c = np.array([(n - 1) / 2.0 + 0.137, (n - 1) / 2.0 - 0.211, (n - 1) / 2.0 + 0.319] if center is None else center)
+
+    def fn(a, b):
+        th = 2 * np.pi * a / nu
+        ph = np.pi * b / nv
+        return np.stack([c[0] + r * np.sin(ph) * np.cos(th), c[1] + r * np.sin(ph) * np.sin(th), c[2] + r * np.cos(ph)], 1)
+
+    return _param_mesh(fn, nu, nv, False)
+
+
+def torus_mesh(n: int, major: float | None = None, minor: float | None = None, nu: int = 128, nv: int = 64, center=None):
+    """Closed torus, axis z, radii scale like synth.torus (88 / 38 at n = 256)."""
+    R = 88.0 * n / 256.0 if major is None else major
+    r = 38.0 * n / 256.0 if minor is None else minor
+    c = np.array([(n - 1) / 2.0 + 0.25, (n - 1) / 2.0 - 0.125, (n - 1) / 2.0 + 0.0625] if center is None else center)
+
+    def fn(a, b):
+        th = 2 * np.pi * a / nu
+        ph = 2 * np.pi * b / nv
+        q = R + r * np.cos(ph)
+        return np.stack([c[0] + q * np.cos(th), c[1] + q * np.sin(th), c[2] + r * np.sin(ph)], 1)
+
+    return _param_mesh(fn, nu, nv, True)
+
+
+def box_mesh(lo, hi):
+    """Axis-aligned box with 12 triangles.  With integer / half-integer corners every face is seen
+    edge-on or passes exactly through voxel centres and column points: the tie rules decide."""
+    lo = np.asarray(lo, np.float32)
+    hi = np.asarray(hi, np.float32)
+    v = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float32)
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    t = []
+    for a, b, c, d in quads:
+        t += [(a, b, c), (a, c, d)]
+    return v, np.asarray(t, np.uint32)
+
+
+def twist_mesh(n: int, nu: int = 256):
+    """The twisted thin plate of synth.twist as a closed mesh: a 0.78 n x 0.39 n x 6 slab whose cross
+    section rotates 180 degrees along x."""
+    L, W, H = 0.78 * n, 0.39 * n, 6.0
+    c = (n - 1) / 2.0
+    ring = np.array([(-W / 2, -H / 2), (W / 2, -H / 2), (W / 2, H / 2), (-W / 2, H / 2)])
+    verts = []
+    for i in range(nu + 1):
+        t = i / nu
+        ang = np.pi * t
+        ca, sa = np.cos(ang), np.sin(ang)
+        for (y, z) in ring:
+            verts.append((c - L / 2 + L * t + 0.031, c + ca * y - sa * z + 0.017, c + sa * y + ca * z - 0.043))
+    tris = []
+    for i in range(nu):
+        for k in range(4):
+            a, b = 4 * i + k, 4 * i + (k + 1) % 4
+            tris += [(a, b, b + 4), (a, b + 4, a + 4)]
+    e = 4 * nu
+    tris += [(0, 2, 1), (0, 3, 2), (e, e + 1, e + 2), (e, e + 2, e + 3)]
+    return np.asarray(verts, np.float32), np.asarray(tris, np.uint32)
