@@ -124,6 +124,16 @@ int vc_closest_grid(vc_ctx* ctx, int32_t* id_out, uint32_t* d2x4_out);
  * d2 = squared distance in double. Host pointers. */
 int vc_closest_points(vc_ctx* ctx, const double* q, int64_t n, int32_t* id, double* d2);
 
+/* Fixed-radius query: drop-in for annkFRSearch(q, sqRad, k, idx, dd, 0.0)
+ * (3rdparty/ann/src/kd_fix_rad_search.cpp:58-189; call sites src/voxelapps.cpp:346,353).  sq_rad[i] is
+ * the SQUARED radius, inclusive (dist <= sqRad, :172).  count[i] = number of sites in range (what the
+ * reference's first call with k = 0 returns).  With off != NULL (int64[n+1], off[0] = 0, host) the
+ * rows idx/d2[off[i]..off[i+1]) receive the closest sites in range ordered by (squared distance, site
+ * id), padded with -1 / -1.0 -- the reference's second call with k = count.  count, idx, d2 nullable.
+ * Host pointers. */
+int vc_radius_search(vc_ctx* ctx, const double* q, const double* sq_rad, int64_t n, const int64_t* off, int32_t* count,
+                     int32_t* idx, double* d2);
+
 /* ---- stage 3: medial measures -------------------------------------------------------------------
  * a6/a7 on the dense grid (dictionary in SURVEY section 0): per grid vertex 3 edge cells (+x,+y,+z),
  * 3 face cells (xy,xz,yz) and the cube; lambda(2-set) = MeasureForMA::lambdaForFace
@@ -141,6 +151,23 @@ int vc_vertex_radii(vc_ctx* ctx, const float* v_xyz, int64_t nv, const int32_t* 
  * out[e] = max over items[off[e]..off[e+1]) of value[item] where valid[item] (valid nullable). */
 int vc_segment_max(vc_ctx* ctx, const int32_t* off, const int32_t* items, int64_t n, const float* value,
                    int64_t nvalue, const uint8_t* valid, float* out);
+
+/* ---- K6: the data-parallel part of the thinning --------------------------------
+ * CellComplexThinning::prune (src/ccthin.cpp:201-271) before its first queue pop.  The FIFO loop itself
+ * stays on the host in the reference's code: its order decides the result.
+ * vc_ref_counts: cellcomplex::refCntPerVert / refCntPerEdge (src/cellcomplex.cpp:315-332) as a histogram:
+ * out[b] = #{i : idx[i] == b}, e.g. idx = the 2*|E| edge end points, or the edge lists of all faces. */
+int vc_ref_counts(vc_ctx* ctx, const int32_t* idx, int64_t n, int64_t nbins, int32_t* out);
+/* vc_simple_pairs: the seeding scan (src/ccthin.cpp:246-270).  Edge e with edge_ref[e] == 1 whose first
+ * incident face f = edge_face0[e] has face_to_remove[f] (nullable) or face_measure[f] < f_t gives the
+ * face-edge pair (1, f, e); vertex v with vert_ref[v] == 1 whose first incident edge e = vert_edge0[v]
+ * has edge_measure[e] < l_t gives the edge-vertex pair (0, e, v)  (include/ccthin.h:22-28).
+ * pairs_out receives int32 triples (type, idx0, idx1) in the reference's push order -- all edges
+ * ascending, then all vertices ascending -- at most `cap` of them; *npairs is the full count.
+ * Inputs host or device; pairs_out host or device, nullable (count only). */
+int vc_simple_pairs(vc_ctx* ctx, const int32_t* edge_ref, const int32_t* edge_face0, int64_t ne, const float* face_measure,
+                    const uint8_t* face_to_remove, int64_t nf, float f_t, const int32_t* vert_ref, const int32_t* vert_edge0,
+                    int64_t nv, const float* edge_measure, float l_t, int32_t* pairs_out, int64_t cap, int64_t* npairs);
 
 /* ---- the whole hot path in one call ----------------------------------------------------------------
  * classify -> sites -> closest -> measures on the resident volume, all results left in device

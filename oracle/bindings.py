@@ -77,6 +77,11 @@ def oracle():
                                                _f32p, _f32p, _f32p, C.c_void_p]
         lib.orc_classify_mesh.argtypes = [_f32p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p]
         lib.orc_classify_mesh.restype = C.c_int
+        lib.orc_radius_search.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_ref_counts.argtypes = [_i32p, C.c_int64, C.c_int64, _i32p]
+        lib.orc_simple_pairs.argtypes = [_i32p, _i32p, C.c_int64, _f32p, C.c_void_p, C.c_float, _i32p, _i32p, C.c_int64, _f32p,
+                                         C.c_float, _i32p]
+        lib.orc_simple_pairs.restype = C.c_int64
         _oracle = lib
     return _oracle
 
@@ -151,6 +156,40 @@ def classify_mesh(verts, tris, nx, ny, nz, M=None):
     rc = oracle().orc_classify_mesh(verts, len(verts), tris.ctypes.data, len(tris), None if m is None else m.ctypes.data,
                                     nx, ny, nz, out)
     return rc, out
+
+
+def radius_search(sites, q, sq_rad, fetch=True):
+    """orc_radius_search: counts, and (CSR) ids / squared distances of every site within sq_rad[i]."""
+    s = np.ascontiguousarray(sites, np.float64).reshape(-1, 3)
+    q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(sq_rad, np.float64), (len(q),)))
+    cnt = np.empty(len(q), np.int32)
+    oracle().orc_radius_search(s, len(s), q, len(q), r, None, cnt.ctypes.data, None, None)
+    if not fetch:
+        return cnt
+    off = np.zeros(len(q) + 1, np.int64)
+    np.cumsum(cnt, out=off[1:])
+    idx = np.empty(max(int(off[-1]), 1), np.int32)
+    d2 = np.empty(max(int(off[-1]), 1), np.float64)
+    oracle().orc_radius_search(s, len(s), q, len(q), r, off.ctypes.data, None, idx.ctypes.data, d2.ctypes.data)
+    return cnt, off, idx[: off[-1]], d2[: off[-1]]
+
+
+def ref_counts(idx, nbins):
+    i = np.ascontiguousarray(idx, np.int32).ravel()
+    out = np.empty(nbins, np.int32)
+    oracle().orc_ref_counts(i, len(i), nbins, out)
+    return out
+
+
+def simple_pairs(edge_ref, edge_face0, face_measure, f_t, vert_ref, vert_edge0, edge_measure, l_t, face_to_remove=None):
+    er, ef = (np.ascontiguousarray(a, np.int32) for a in (edge_ref, edge_face0))
+    vr, ve = (np.ascontiguousarray(a, np.int32) for a in (vert_ref, vert_edge0))
+    fm, em = (np.ascontiguousarray(a, np.float32) for a in (face_measure, edge_measure))
+    tr = None if face_to_remove is None else np.ascontiguousarray(face_to_remove, np.uint8)
+    out = np.empty((max(len(er) + len(vr), 1), 3), np.int32)
+    n = oracle().orc_simple_pairs(er, ef, len(er), fm, None if tr is None else tr.ctypes.data, f_t, vr, ve, len(vr), em, l_t, out)
+    return out[:n].copy()
 
 
 def extract_sites(inside: np.ndarray) -> np.ndarray:
@@ -257,6 +296,22 @@ def ref_ann(sites, q, brute=False):
     fn = ref().ref_ann_brute_search if brute else ref().ref_ann_kd_search
     fn(s, len(s), s.shape[1], q, len(q), idx, d2)
     return idx, d2
+
+
+def ref_ann_fr(sites, q, sq_rad):
+    """The reference's two-call pattern (src/voxelapps.cpp:346-353): counts, then every point in range.
+    Returns (counts, list of (ids, d2) per query) straight from ANNkd_tree::annkFRSearch."""
+    s = np.ascontiguousarray(sites, np.float64)
+    q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(sq_rad, np.float64), (len(q),)))
+    cnt = np.empty(len(q), np.int32)
+    ref().ref_ann_kd_fr_search(s, len(s), 3, q, len(q), r, 0, cnt, None, None)
+    kmax = int(cnt.max()) if len(cnt) else 0
+    idx = np.full((len(q), max(kmax, 1)), -1, np.int32)
+    d2 = np.full((len(q), max(kmax, 1)), -1.0, np.float64)
+    if kmax:
+        ref().ref_ann_kd_fr_search(s, len(s), 3, q, len(q), r, kmax, cnt, idx.ctypes.data, d2.ctypes.data)
+    return cnt, idx, d2
 
 
 def ref_lambda(a, b):

@@ -437,3 +437,99 @@ int orc_classify_mesh(const float* verts, int64_t nv, const uint32_t* tris, int6
     free(Q);
     return rc;
 }
+
+/* ---- K6: what CellComplexThinning::prune does before its first queue pop ---------------------------
+ * refCntPerVert / refCntPerEdge (src/cellcomplex.cpp:315-332) count incidences; the seeding scan
+ * (src/ccthin.cpp:246-270) walks edges then vertices in index order and pushes
+ *   (FE_PAIR=1, nbFaceofEdge(e,0), e)  when ref_edge[e]==1 and face_edge_pair_below_threshold
+ *                                      (:514-521: m_to_remove_face[f] || m_measure[FACE][f] < f_t), then
+ *   (EV_PAIR=0, nbEdgeofVert(v,0), v)  when ref_vert[v]==1 and m_measure[EDGE][e] < l_t (:508-512).
+ * Pinned by the queue size the reference CLI prints ("after init, q size", tests/golden/cli_sphere64.txt)
+ * and, end to end, by the thinned .ply/.r of the GPU CLI being byte-identical to the reference's. */
+void orc_ref_counts(const int32_t* idx, int64_t n, int64_t nbins, int32_t* out)
+{
+    memset(out, 0, sizeof(int32_t) * (size_t)nbins);
+    for (int64_t i = 0; i < n; ++i)
+        out[idx[i]]++;
+}
+int64_t orc_simple_pairs(const int32_t* edge_ref, const int32_t* edge_face0, int64_t ne, const float* face_measure,
+                         const uint8_t* face_to_remove, float f_t, const int32_t* vert_ref, const int32_t* vert_edge0,
+                         int64_t nv, const float* edge_measure, float l_t, int32_t* pairs_out)
+{
+    int64_t n = 0;
+    for (int64_t e = 0; e < ne; ++e)
+        if (edge_ref[e] == 1)
+        {
+            int32_t f = edge_face0[e];
+            if ((face_to_remove && face_to_remove[f]) || face_measure[f] < f_t)
+            {
+                pairs_out[3 * n] = 1, pairs_out[3 * n + 1] = f, pairs_out[3 * n + 2] = (int32_t)e;
+                ++n;
+            }
+        }
+    for (int64_t v = 0; v < nv; ++v)
+        if (vert_ref[v] == 1)
+        {
+            int32_t e = vert_edge0[v];
+            if (edge_measure[e] < l_t)
+            {
+                pairs_out[3 * n] = 0, pairs_out[3 * n + 1] = e, pairs_out[3 * n + 2] = (int32_t)v;
+                ++n;
+            }
+        }
+    return n;
+}
+
+/* ---- a5 (fixed radius): ANNkd_tree::annkFRSearch(q, sqRad, k, idx, dd, 0.0) ----------------------
+ * 3rdparty/ann/src/kd_fix_rad_search.cpp:58-189: a point is in range iff its squared distance (double,
+ * x,y,z order) is <= sqRad (:172, inclusive); the call returns the number of points in range and the k
+ * closest of them.  The reference calls it with k = 0 to count, then with k = count
+ * (src/voxelapps.cpp:346-353).  Brute force here; rows are ordered by (distance, id) -- ANN orders
+ * equal distances by traversal, so the pin compares rows as sets of (id, distance).
+ * off == NULL: count only. */
+void orc_radius_search(const double* sites, int64_t ns, const double* q, int64_t nq, const double* sq_rad,
+                       const int64_t* off, int32_t* count, int32_t* idx, double* d2)
+{
+    for (int64_t i = 0; i < nq; ++i)
+    {
+        int cnt = 0, have = 0;
+        int cap = off ? (int)(off[i + 1] - off[i]) : 0;
+        int32_t* ri = off ? idx + off[i] : NULL;
+        double* rd = off ? d2 + off[i] : NULL;
+        for (int k = 0; k < cap; ++k)
+            ri[k] = -1, rd[k] = -1.0;
+        for (int64_t s = 0; s < ns; ++s)
+        {
+            double d = 0;
+            for (int a = 0; a < 3; ++a)
+            {
+                double t = q[3 * i + a] - sites[3 * s + a];
+                d = d + t * t;
+            }
+            if (!(d <= sq_rad[i]))
+                continue;
+            ++cnt;
+            if (!cap)
+                continue;
+            int pos = have;
+            if (have == cap)
+            {
+                if (!(d < rd[cap - 1])) /* ids ascend, so an equal distance never displaces */
+                    continue;
+                pos = cap - 1;
+            }
+            else
+                ++have;
+            while (pos > 0 && rd[pos - 1] > d)
+            {
+                rd[pos] = rd[pos - 1];
+                ri[pos] = ri[pos - 1];
+                --pos;
+            }
+            rd[pos] = d;
+            ri[pos] = (int32_t)s;
+        }
+        if (count)
+            count[i] = cnt;
+    }
+}

@@ -113,6 +113,26 @@ def pipeline():
         v_msure=p2["v_msure"], e_msure=p2["e_msure"], f_msure=p2["f_msure"])
 
 
+def fr_search():
+    """annkFRSearch (a5, fixed radius; src/voxelapps.cpp:346-353) from the REAL ANNkd_tree: lattice sites
+    of a small sphere (many equal distances; radii that hit a distance exactly, the inclusive case) and
+    random points.  Stored per query: count and the (id, d2) rows sorted by (d2, id)."""
+    sites = ob.ref_extract_sites(synth.sphere(16)).astype(np.float64)
+    rng = np.random.default_rng(4242)
+    q = np.concatenate([rng.uniform(-1, 17, (150, 3)), np.floor(rng.uniform(0, 16, (150, 3)))])
+    _, nn_d2 = ob.ref_ann(sites, q)
+    # the reference's radius: nearest squared distance + eps (exactly-on-the-sphere ties), plus larger balls
+    sq = np.concatenate([nn_d2[:100] + 1e-7, nn_d2[100:200], rng.uniform(0, 30, 100)])
+    cnt, idx, d2 = ob.ref_ann_fr(sites, q, sq)
+    rows_i, rows_d = [], []
+    for i in range(len(q)):
+        o = np.lexsort((idx[i, : cnt[i]], d2[i, : cnt[i]]))
+        rows_i.append(idx[i, : cnt[i]][o])
+        rows_d.append(d2[i, : cnt[i]][o])
+    np.savez_compressed(os.path.join(OUT, "ann_fr_search.npz"), sites=sites, q=q, sq_rad=sq, count=cnt,
+                        idx=np.concatenate(rows_i), d2=np.concatenate(rows_d))
+
+
 def cli_sphere64():
     """BASELINE config 1: sphere64 through the unmodified main_voroUtility -md=vol2ma; output file
     hashes and the counts the CLI prints (26224/43250/17027 -> 8955/20138/11184,
@@ -142,5 +162,6 @@ if __name__ == "__main__":
     ann_tests()
     sites_and_closest()
     pipeline()
+    fr_search()
     cli_sphere64()
     print("golden fixtures written to", OUT)

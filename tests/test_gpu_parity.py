@@ -309,3 +309,32 @@ def test_errors_are_reported(ctx_factory):
         c.closest_grid()  # no sites
     with pytest.raises(api.VoxcoreError):
         c.set_grid(4096, 8, 8)
+
+
+# ---- fixed-radius query (annkFRSearch drop-in) ----------------------------------------------------
+def test_radius_search_golden_inputs(ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ann_fr_search.npz"))
+    ctx.set_grid(16, 16, 16)
+    ctx.set_sites(g["sites"].astype(np.float32))
+    cnt, off, idx, d2 = ctx.radius_search(g["q"], g["sq_rad"])
+    assert np.array_equal(cnt, g["count"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(d2, g["d2"])
+
+
+def test_radius_search_general_sites_and_edge_radii(ctx):
+    rng = np.random.default_rng(5)
+    sites = rng.uniform(0, 40, (5000, 3)).astype(np.float32)
+    q = rng.uniform(-5, 45, (3000, 3))
+    sq = rng.uniform(0, 25, 3000)
+    sq[:10] = 0.0          # only an exact hit is in range
+    sq[10:20] = -1.0       # nothing is
+    sq[20:24] = 1e9        # everything is
+    q[:5] = sites[:5].astype(np.float64)  # exact hits (self matches are allowed, ANN_ALLOW_SELF_MATCH)
+    ctx.set_grid(40, 40, 40)
+    ctx.set_sites(sites)
+    cnt, off, idx, d2 = ctx.radius_search(q, sq)
+    ocnt, ooff, oidx, od2 = ob.radius_search(sites.astype(np.float64), q, sq)
+    assert np.array_equal(cnt, ocnt) and (cnt[:5] >= 1).all() and (cnt[10:20] == 0).all() and (cnt[20:24] == 5000).all()
+    assert np.array_equal(idx, oidx) and np.array_equal(d2, od2)
+    assert np.array_equal(ctx.radius_search(q, sq, fetch=False), ocnt)

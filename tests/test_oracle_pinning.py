@@ -107,3 +107,28 @@ def test_oracle_vs_live_reference(name):
     both = np.concatenate([a, b])
     pairs[:, 1] += 4000
     assert np.array_equal(ob.face_lambda(both, pairs), ob.ref_lambda(a, b))
+
+
+def test_fixed_radius_search_golden():
+    """annkFRSearch (src/voxelapps.cpp:346-353): counts and the full in-range rows of the REAL ANNkd_tree
+    (tests/golden/ann_fr_search.npz) -- inclusive radius, rows compared in (distance, id) order."""
+    g = np.load(os.path.join(G, "ann_fr_search.npz"))
+    cnt, off, idx, d2 = ob.radius_search(g["sites"], g["q"], g["sq_rad"])
+    assert np.array_equal(cnt, g["count"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(d2, g["d2"])
+    assert (cnt[100:200] >= 1).all()  # radius == nearest distance exactly: the nearest site is in range
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built")
+def test_fixed_radius_search_vs_live_reference():
+    rng = np.random.default_rng(99)
+    sites = rng.uniform(0, 10, (400, 3))
+    q = rng.uniform(-1, 11, (200, 3))
+    sq = rng.uniform(0, 9, 200)
+    rc, ri, rd = ob.ref_ann_fr(sites, q, sq)
+    cnt, off, idx, d2 = ob.radius_search(sites, q, sq)
+    assert np.array_equal(cnt, rc)
+    for i in range(len(q)):
+        o = np.lexsort((ri[i, : rc[i]], rd[i, : rc[i]]))
+        assert np.array_equal(idx[off[i]:off[i + 1]], ri[i, : rc[i]][o])
+        assert np.array_equal(d2[off[i]:off[i + 1]], rd[i, : rc[i]][o])

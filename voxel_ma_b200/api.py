@@ -24,7 +24,7 @@ SYMBOLS = [
     "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_f64_zfast",
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_closest_grid",
-    "vc_closest_points", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max",
+    "vc_closest_points", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
@@ -77,10 +77,13 @@ def load_library(path: str | None = None):
     lib.vc_sites_import_global.argtypes = [vp, vp, vp, i64]
     lib.vc_closest_grid.argtypes = [vp, vp, vp]
     lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_radius_search.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.vc_cell_measures_grid.argtypes = [vp, vp, vp, vp, vp]
     lib.vc_face_lambda.argtypes = [vp, vp, i64, vp]
     lib.vc_vertex_radii.argtypes = [vp, vp, i64, vp, vp]
     lib.vc_segment_max.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp]
+    lib.vc_ref_counts.argtypes = [vp, vp, i64, i64, vp]
+    lib.vc_simple_pairs.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.c_float, vp, vp, i64, vp, C.c_float, vp, i64, C.POINTER(i64)]
     lib.vc_run_dense.argtypes = [vp, C.POINTER(i64)]
     lib.vc_closest_and_measures.argtypes = [vp]
     lib.vc_set_pipeline.argtypes = [vp, i32, i32]
@@ -250,6 +253,21 @@ class Context:
         self._ck(self.lib.vc_closest_points(self.h, _ptr(q), len(q), _ptr(ids), _ptr(d2)))
         return ids, d2
 
+    def radius_search(self, q, sq_rad, fetch=True):
+        """annkFRSearch drop-in: counts, then (CSR) ids / squared distances of all sites within sq_rad[i]."""
+        p = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(sq_rad, np.float64), (len(p),)))
+        cnt = np.empty(len(p), np.int32)
+        self._ck(self.lib.vc_radius_search(self.h, _ptr(p), _ptr(r), len(p), None, _ptr(cnt), None, None))
+        if not fetch:
+            return cnt
+        off = np.zeros(len(p) + 1, np.int64)
+        np.cumsum(cnt, out=off[1:])
+        idx = np.empty(max(int(off[-1]), 1), np.int32)
+        d2 = np.empty(max(int(off[-1]), 1), np.float64)
+        self._ck(self.lib.vc_radius_search(self.h, _ptr(p), _ptr(r), len(p), _ptr(off), None, _ptr(idx), _ptr(d2)))
+        return cnt, off, idx[: off[-1]], d2[: off[-1]]
+
     def cell_measures_grid(self, fetch=True):
         s = self.slab_shape
         if fetch:
@@ -284,6 +302,26 @@ class Context:
         return out
 
     # ---- whole path
+    def ref_counts(self, idx, nbins):
+        """K6: cellcomplex::refCntPerVert / refCntPerEdge as a histogram of incidence indices."""
+        i = np.ascontiguousarray(idx, np.int32).ravel()
+        out = np.empty(nbins, np.int32)
+        self._ck(self.lib.vc_ref_counts(self.h, _ptr(i), len(i), nbins, _ptr(out)))
+        return out
+
+    def simple_pairs(self, edge_ref, edge_face0, face_measure, f_t, vert_ref, vert_edge0, edge_measure, l_t, face_to_remove=None):
+        """K6: the queue seeding of CellComplexThinning::prune; returns int32 (n, 3) rows (type, idx0, idx1)."""
+        er, ef = (np.ascontiguousarray(a, np.int32) for a in (edge_ref, edge_face0))
+        vr, ve = (np.ascontiguousarray(a, np.int32) for a in (vert_ref, vert_edge0))
+        fm, em = (np.ascontiguousarray(a, np.float32) for a in (face_measure, edge_measure))
+        tr = None if face_to_remove is None else np.ascontiguousarray(face_to_remove, np.uint8)
+        n = C.c_int64(0)
+        cap = len(er) + len(vr)
+        out = np.empty((max(cap, 1), 3), np.int32)
+        self._ck(self.lib.vc_simple_pairs(self.h, _ptr(er), _ptr(ef), len(er), _ptr(fm), _ptr(tr), len(fm), C.c_float(f_t), _ptr(vr),
+                                          _ptr(ve), len(vr), _ptr(em), C.c_float(l_t), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].copy()
+
     def run_dense(self) -> int:
         n = C.c_int64()
         self._ck(self.lib.vc_run_dense(self.h, C.byref(n)))

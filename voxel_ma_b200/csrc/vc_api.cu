@@ -481,6 +481,33 @@ extern "C"
         return st_segment_max(c, off, items, n, value, nvalue, valid, out);
     }
 
+    int vc_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n, const int64_t* off, int32_t* count, int32_t* idx,
+                         double* d2)
+    {
+        if (!c || n < 0 || (n > 0 && (!q || !sq_rad)))
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        return st_radius_search(c, q, sq_rad, n, off, count, idx, d2);
+    }
+    int vc_ref_counts(vc_ctx* c, const int32_t* idx, int64_t n, int64_t nbins, int32_t* out)
+    {
+        if (!c || n < 0 || nbins < 0 || (n > 0 && !idx) || (nbins > 0 && !out))
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        return st_ref_counts(c, idx, n, nbins, out);
+    }
+    int vc_simple_pairs(vc_ctx* c, const int32_t* edge_ref, const int32_t* edge_face0, int64_t ne, const float* face_measure,
+                        const uint8_t* face_to_remove, int64_t nf, float f_t, const int32_t* vert_ref, const int32_t* vert_edge0,
+                        int64_t nv, const float* edge_measure, float l_t, int32_t* pairs_out, int64_t cap, int64_t* npairs)
+    {
+        if (!c || ne < 0 || nf < 0 || nv < 0 || cap < 0 || (ne > 0 && (!edge_ref || !edge_face0 || !edge_measure)) ||
+            (nf > 0 && !face_measure) || (nv > 0 && (!vert_ref || !vert_edge0)))
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        return st_simple_pairs(c, edge_ref, edge_face0, ne, face_measure, face_to_remove, nf, f_t, vert_ref, vert_edge0, nv,
+                               edge_measure, l_t, pairs_out, cap, npairs);
+    }
+
     int vc_run_dense(vc_ctx* c, int64_t* nsites)
     {
         if (!c)

@@ -161,12 +161,18 @@ int st_face_lambda(vc_ctx* c, const int32_t* pairs, int64_t nf, float* out);
 int st_vertex_radii(vc_ctx* c, const float* v, int64_t nv, const int32_t* site_of_v, float* out);
 int st_segment_max(vc_ctx* c, const int32_t* off, const int32_t* items, int64_t n, const float* value,
                    int64_t nvalue, const uint8_t* valid, float* out);
+int st_ref_counts(vc_ctx* c, const int32_t* idx, int64_t n, int64_t nbins, int32_t* out);
+int st_simple_pairs(vc_ctx* c, const int32_t* edge_ref, const int32_t* edge_face0, int64_t ne, const float* face_measure,
+                    const uint8_t* face_to_remove, int64_t nf, float f_t, const int32_t* vert_ref, const int32_t* vert_edge0,
+                    int64_t nv, const float* edge_measure, float l_t, int32_t* pairs_out, int64_t cap, int64_t* npairs);
 int st_upload_f64_zfast(vc_ctx* c, const double* vol);
 int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* tris, int64_t nt, const double* M);
 // general sites
 int st_build_cell_list(vc_ctx* c, const float* xyz_host, int64_t n);
 int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double* d2);
 int st_closest_general_grid(vc_ctx* c);
+int st_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n, const int64_t* off, int32_t* count, int32_t* idx,
+                     double* d2);
 
 // radix sort of (u64 key, u32 value) pairs on bits [0,nbits); result pointers returned
 int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io);

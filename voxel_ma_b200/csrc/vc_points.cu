@@ -333,6 +333,145 @@ int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double
     return VC_OK;
 }
 
+// =============================================================================================
+// Fixed-radius query: drop-in for ANNkd_tree::annkFRSearch(q, sqRad, k, idx, dd, eps=0)
+// (3rdparty/ann/src/kd_fix_rad_search.cpp:58-189; call sites src/voxelapps.cpp:346,353).
+// A site is in range iff its squared distance (double, terms accumulated x,y,z) is <= sqRad
+// (inclusive, :172; ANN's early exit on a partial sum is the same predicate because the partial sums
+// never exceed the total).  count = number of sites in range; the row off[i]..off[i+1] receives the
+// (off[i+1]-off[i]) closest of them ordered by (squared distance, site id), -1 / -1.0 padded.  ANN
+// orders equal distances by its traversal; the reference only ever asks for ALL sites in range and
+// uses them as a set, so the deterministic order here is a refinement, not a difference.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+    k_radius_search(const double* __restrict__ q, const double* __restrict__ sq_rad, int64_t n, CellGrid g, const int* __restrict__ ptr,
+                    const double* __restrict__ ps, const int* __restrict__ ent, const int64_t* __restrict__ off, int* __restrict__ count,
+                    int* __restrict__ idx, double* __restrict__ dd)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double q0 = q[3 * i], q1 = q[3 * i + 1], q2 = q[3 * i + 2], R2 = sq_rad[i];
+    int cnt = 0;
+    int64_t row0 = 0;
+    int cap = 0, have = 0;
+    if (off)
+    {
+        row0 = off[i];
+        cap = (int)(off[i + 1] - off[i]);
+        for (int k = 0; k < cap; ++k)
+        {
+            idx[row0 + k] = -1;
+            dd[row0 + k] = -1.0;
+        }
+    }
+    if (R2 >= 0.0)
+    { // cells the ball can reach (radius padded by one part in 1e9 against the rounding of sqrt and of the cell map)
+        const double r = sqrt(R2) * (1.0 + 1e-9) + 1e-300;
+        const int xl = cg_cell(g, q0 - r, 0), xh = cg_cell(g, q0 + r, 0);
+        const int yl = cg_cell(g, q1 - r, 1), yh = cg_cell(g, q1 + r, 1);
+        const int zl = cg_cell(g, q2 - r, 2), zh = cg_cell(g, q2 + r, 2);
+        for (int z = zl; z <= zh; ++z)
+            for (int y = yl; y <= yh; ++y)
+            {
+                const int64_t rowc = ((int64_t)z * g.dim[1] + y) * g.dim[0];
+                const int b = ptr[rowc + xl], e = ptr[rowc + xh + 1]; // the x-run is contiguous in the list
+                for (int k = b; k < e; ++k)
+                {
+                    double t = __dsub_rn(q0, ps[3 * k]);
+                    double d = __dmul_rn(t, t);
+                    t = __dsub_rn(q1, ps[3 * k + 1]);
+                    d = __dadd_rn(d, __dmul_rn(t, t));
+                    t = __dsub_rn(q2, ps[3 * k + 2]);
+                    d = __dadd_rn(d, __dmul_rn(t, t));
+                    if (!(d <= R2))
+                        continue;
+                    ++cnt;
+                    if (!cap)
+                        continue;
+                    const int id = ent[k];
+                    // insertion into the sorted row (distance, id); the last one falls off when full
+                    int pos = have;
+                    if (have == cap)
+                    {
+                        const double dl = dd[row0 + cap - 1];
+                        const int il = idx[row0 + cap - 1];
+                        if (!(d < dl || (d == dl && id < il)))
+                            continue;
+                        pos = cap - 1;
+                    }
+                    else
+                        ++have;
+                    while (pos > 0)
+                    {
+                        const double dp = dd[row0 + pos - 1];
+                        const int ip = idx[row0 + pos - 1];
+                        if (dp < d || (dp == d && ip < id))
+                            break;
+                        dd[row0 + pos] = dp;
+                        idx[row0 + pos] = ip;
+                        --pos;
+                    }
+                    dd[row0 + pos] = d;
+                    idx[row0 + pos] = id;
+                }
+            }
+    }
+    if (count)
+        count[i] = cnt;
+}
+
+int st_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n, const int64_t* off, int32_t* count, int32_t* idx,
+                     double* d2)
+{
+    if (!c->have_sites)
+        return vc_fail(c, VC_ERR_STATE, "vc_radius_search needs sites");
+    if (n == 0)
+        return VC_OK;
+    VC_TRY(ensure_cell_list(c));
+    const int64_t total = off ? off[n] : 0;
+    if (off && (off[0] != 0 || total < 0))
+        return vc_fail(c, VC_ERR_INVALID, "vc_radius_search: off must start at 0 and be non-decreasing");
+    DevBuf dq, dr, doff, dcnt, didx, ddd;
+    cudaError_t e = dq.ensure((size_t)n * 24);
+    if (e == cudaSuccess)
+        e = dr.ensure((size_t)n * 8);
+    if (e == cudaSuccess)
+        e = dcnt.ensure((size_t)n * 4);
+    if (e == cudaSuccess && off)
+    {
+        e = doff.ensure((size_t)(n + 1) * 8);
+        if (e == cudaSuccess)
+            e = didx.ensure((size_t)(total > 0 ? total : 1) * 4);
+        if (e == cudaSuccess)
+            e = ddd.ensure((size_t)(total > 0 ? total : 1) * 8);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(doff.p, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dq.p, q, (size_t)n * 24, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dr.p, sq_rad, (size_t)n * 8, cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess)
+    {
+        VC_LAUNCH(c, "radius_search", k_radius_search, vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), dr.as<double>(), n, g_of(c),
+                  c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), off ? doff.as<int64_t>() : (const int64_t*)nullptr,
+                  dcnt.as<int>(), didx.as<int>(), ddd.as<double>());
+        if (count)
+            e = cudaMemcpyAsync(count, dcnt.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess && off && total > 0 && idx)
+            e = cudaMemcpyAsync(idx, didx.p, (size_t)total * 4, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess && off && total > 0 && d2)
+            e = cudaMemcpyAsync(d2, ddd.p, (size_t)total * 8, cudaMemcpyDefault, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    dq.release(), dr.release(), doff.release(), dcnt.release(), didx.release(), ddd.release();
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "radius_search", e);
+    return VC_OK;
+}
+
 // arbitrary (non-lattice) site set queried at every grid vertex of the slab
 int st_closest_general_grid(vc_ctx* c)
 {
