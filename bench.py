@@ -291,7 +291,12 @@ def run_ours(args):
             state["nsites"] = ctx.run_dense()
             return
         ctx.classify_grid(fetch=False)
+        if state.get("peers") is not None:  # records stored straight into every rank's memory over NVLink
+            state["nsites"] = state["peers"].exchange()
+            ctx.closest_and_measures()
+            return
         n = ctx.sites_detect_local()
+        state["nlocal"] = n
         keys = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
         corners = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
         ctx.sites_export_local(keys.data_ptr(), corners.data_ptr())
@@ -307,6 +312,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         ctx.synchronize()
 
+    if world > 1 and args.exchange == "peers":
+        # one step over NCCL first: it sizes the receive regions and is the cross-check of the peer path
+        step()
+        ctx.synchronize()
+        ref_sites = ctx.get_sites()
+        t = torch.tensor([state["nlocal"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        state["peers"] = slabs.PeerExchange(ctx, 2 * int(t[0]) + 4096)
+        step()
+        ctx.synchronize()
+        if not np.array_equal(ctx.get_sites(), ref_sites):
+            raise SystemExit("peer-memory exchange and NCCL all-gather disagree on the site numbering")
+        del ref_sites
     for _ in range(max(args.warmup, 3)):
         step()
     # ---- timed region: exactly K steps, CUDA events on the stream the kernels are launched on
@@ -407,7 +425,10 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32",
             "data": "synthetic",
             "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world,
-                       "vertices_per_gpu": nv_local, "l2": "inputs larger than L2 (no flush needed)",
+                       "vertices_per_gpu": nv_local,
+                       "exchange": ("none (one slab)" if world == 1 else
+                                    "peer memory: detection kernel stores records into every rank over NVLink (vc_peer.cu)"
+                                    if state.get("peers") is not None else "NCCL all-gather"), "l2": "inputs larger than L2 (no flush needed)",
                        "outputs": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32"},
             "e2e": {"value": nv_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
@@ -441,6 +462,8 @@ def main():
     ap.add_argument("--workload", default=None, help="sphere256 | torus256 | twist512 | assembly1024 ...")
     ap.add_argument("--grid", default=None, help="NX,NY,NZ (assembly family)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peers", choices=["peers", "nccl"],
+                    help="N>1: how the site records travel between ranks (peer-memory kernel stores, or NCCL all-gather)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -110,6 +110,26 @@ int64_t vc_num_sites(const vc_ctx* ctx);
 int vc_sites_detect_local(vc_ctx* ctx, int64_t* nlocal);
 int vc_sites_export_local(vc_ctx* ctx, uint64_t* keys_out, uint64_t* corners_out);
 int vc_sites_import_global(vc_ctx* ctx, const uint64_t* keys, const uint64_t* corners, int64_t n);
+/* The same exchange over peer memory (NVLink), without a collective library on the data path: the
+ * detection kernel stores every record straight into the receive buffer of every rank of the slab
+ * group, one warp posts (sequence, count) with a system-scope release, and a rank collects by
+ * waiting on its own header (voxel_ma_b200/csrc/vc_peer.cu).  Set-up, once per group:
+ *   vc_peer_create   allocates this rank's receive buffer for `world` ranks x `cap` records each and
+ *                    writes its 64-byte CUDA IPC handle to handle_out (nullable);
+ *   vc_peer_open     maps the other ranks' buffers from `handles` (world x 64 bytes, rank order;
+ *                    one process per GPU: the handles travel once over torch.distributed / MPI);
+ *   vc_peer_open_ptrs  same for contexts living in ONE process: bases[p] = vc_peer_buffer of rank p.
+ * Per exchange (needs vc_classify_grid): vc_sites_post_peers is asynchronous; vc_sites_collect_peers
+ * waits for all ranks' records, numbers the union (same result as vc_sites_import_global) and
+ * returns the global site count.  A rank that never posts turns into VC_ERR_STATE after ~2 s, a
+ * rank with more than `cap` records into VC_ERR_NOMEM; neither hangs. */
+int vc_peer_create(vc_ctx* ctx, int world, int rank, int64_t cap, void* handle_out);
+int vc_peer_open(vc_ctx* ctx, const void* handles);
+int vc_peer_open_ptrs(vc_ctx* ctx, void* const* bases);
+void* vc_peer_buffer(vc_ctx* ctx);
+int vc_peer_close(vc_ctx* ctx);
+int vc_sites_post_peers(vc_ctx* ctx);
+int vc_sites_collect_peers(vc_ctx* ctx, int64_t* n_all);
 
 /* ---- stage 2: closest site ----------------------------------------------------------------------
  * a5: the operator the reference gets from ANN, annkSearch(k=1, eps=0)

@@ -199,6 +199,75 @@ def test_slab_contexts_pipelined_second_half(ctx_factory):
         assert np.array_equal(p.download(api.ARR_CUBE), oc[z0:z1]) and np.array_equal(p.download(api.ARR_RADIUS), orad[z0:z1])
 
 
+def test_peer_exchange_matches_the_gathered_import(ctx_factory):
+    """the exchange over peer memory (vc_peer.cu): records stored straight into every rank's receive
+    buffer, posted with a release store, collected by waiting on the own header.  Three slab contexts
+    of one process (vc_peer_open_ptrs), three exchanges in a row (both parities of the double
+    buffer, and a changed volume in between), results == oracle."""
+    vol = synth.twist(40)
+    nz, ny, nx = vol.shape
+    cuts = [0, 9, 10, 40]
+    world = len(cuts) - 1
+    parts = [ctx_factory() for _ in range(world)]
+    for k, p in enumerate(parts):
+        p.set_grid(nx, ny, nz, cuts[k], cuts[k + 1])
+        p.peer_create(world, k, 20000)
+    bases = [p.peer_buffer() for p in parts]
+    for p in parts:
+        p.peer_open_ptrs(bases)
+    for it, v in enumerate([vol, synth.assembly(40, count=10), vol]):
+        o_inside = ob.classify_grid(v)
+        o_sites = ob.extract_sites(o_inside)
+        o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
+        for k, p in enumerate(parts):
+            z0, z1 = cuts[k], cuts[k + 1]
+            lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
+            p.upload_volume(v[lo:hi], zlo=lo)
+            p.classify_grid(fetch=False)
+            p.sites_post_peers()  # asynchronous: nobody waits before everybody has posted
+        for k, p in enumerate(parts):
+            z0, z1 = cuts[k], cuts[k + 1]
+            assert p.sites_collect_peers() == len(o_sites)
+            assert np.array_equal(p.get_sites(), o_sites)
+            p.closest_and_measures()
+            assert np.array_equal(p.download(api.ARR_ID), o_ids[z0:z1]) and np.array_equal(p.download(api.ARR_D2X4), o_d2[z0:z1])
+    for p in parts:
+        p.peer_close()
+
+
+def test_peer_exchange_errors_do_not_hang(ctx_factory):
+    """a rank that never posts -> VC_ERR_STATE after the bounded wait; too small a capacity -> VC_ERR_NOMEM"""
+    vol = synth.twist(24)
+    nz, ny, nx = vol.shape
+
+    def pair(cap):
+        a, b = ctx_factory(), ctx_factory()
+        for k, p in enumerate((a, b)):
+            z0, z1 = [0, 12][k], [12, 24][k]
+            p.set_grid(nx, ny, nz, z0, z1)
+            p.peer_create(2, k, cap)
+            p.upload_volume(vol[max(z0 - 1, 0):min(z1 + 1, nz)], zlo=max(z0 - 1, 0))
+            p.classify_grid(fetch=False)
+        bases = [a.peer_buffer(), b.peer_buffer()]
+        a.peer_open_ptrs(bases)
+        b.peer_open_ptrs(bases)
+        return a, b
+
+    a, b = pair(20000)
+    a.sites_post_peers()
+    with pytest.raises(api.VoxcoreError, match="timed out"):
+        a.sites_collect_peers()  # b has not posted
+    b.sites_post_peers()
+    assert b.sites_collect_peers() == len(ob.extract_sites(ob.classify_grid(vol)))  # a's post is still there
+    a, b = pair(16)
+    a.sites_post_peers()
+    b.sites_post_peers()
+    with pytest.raises(api.VoxcoreError, match="capacity"):
+        a.sites_collect_peers()
+    with pytest.raises(api.VoxcoreError, match="no peer group"):
+        ctx_factory().sites_post_peers()
+
+
 @pytest.mark.parametrize("fam,n", [("twist", 256), ("torus", 256), ("assembly", 200)])
 def test_full_size_properties(ctx_factory, fam, n):
     """sizes the CPU oracle cannot finish: size-independent properties instead.

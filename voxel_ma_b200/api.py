@@ -23,7 +23,8 @@ SYMBOLS = [
     "vc_abi_version", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
     "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_f64_zfast",
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
-    "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_closest_grid",
+    "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
+    "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
@@ -75,6 +76,14 @@ def load_library(path: str | None = None):
     lib.vc_sites_detect_local.argtypes = [vp, C.POINTER(i64)]
     lib.vc_sites_export_local.argtypes = [vp, vp, vp]
     lib.vc_sites_import_global.argtypes = [vp, vp, vp, i64]
+    lib.vc_peer_create.argtypes = [vp, i32, i32, i64, vp]
+    lib.vc_peer_open.argtypes = [vp, vp]
+    lib.vc_peer_open_ptrs.argtypes = [vp, vp]
+    lib.vc_peer_buffer.argtypes = [vp]
+    lib.vc_peer_buffer.restype = vp
+    lib.vc_peer_close.argtypes = [vp]
+    lib.vc_sites_post_peers.argtypes = [vp]
+    lib.vc_sites_collect_peers.argtypes = [vp, C.POINTER(i64)]
     lib.vc_closest_grid.argtypes = [vp, vp, vp]
     lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
     lib.vc_radius_search.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
@@ -239,6 +248,38 @@ class Context:
 
     def sites_import_global(self, keys, corners, n):
         self._ck(self.lib.vc_sites_import_global(self.h, _ptr(keys), _ptr(corners), n))
+
+    # ---- the exchange over peer memory (csrc/vc_peer.cu)
+    def peer_create(self, world: int, rank: int, cap: int) -> bytes:
+        """Allocate this rank's receive buffer; returns its 64-byte CUDA IPC handle."""
+        h = C.create_string_buffer(64)
+        self._ck(self.lib.vc_peer_create(self.h, world, rank, cap, C.cast(h, C.c_void_p)))
+        return h.raw
+
+    def peer_open(self, handles) -> None:
+        """handles: the IPC handles of all ranks in rank order (one process per GPU)."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.lib.vc_peer_open(self.h, C.cast(buf, C.c_void_p)))
+
+    def peer_open_ptrs(self, bases) -> None:
+        """bases: receive-buffer pointers of all ranks (contexts of one process)."""
+        arr = (C.c_void_p * len(bases))(*bases)
+        self._ck(self.lib.vc_peer_open_ptrs(self.h, C.cast(arr, C.c_void_p)))
+
+    def peer_buffer(self) -> int:
+        return self.lib.vc_peer_buffer(self.h)
+
+    def peer_close(self) -> None:
+        self._ck(self.lib.vc_peer_close(self.h))
+
+    def sites_post_peers(self) -> None:
+        self._ck(self.lib.vc_sites_post_peers(self.h))
+
+    def sites_collect_peers(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_sites_collect_peers(self.h, C.byref(n)))
+        return n.value
 
     def closest_grid(self, fetch=True):
         ids = np.empty(self.slab_shape, np.int32) if fetch else None

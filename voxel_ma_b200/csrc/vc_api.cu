@@ -143,6 +143,7 @@ extern "C"
         prof_resolve(c);
         for (auto e : c->ev_pool)
             cudaEventDestroy(e);
+        vc_peer_release(c);
         DevBuf* bufs[] = {&c->vol, &c->inside, &c->bits, &c->cand_key, &c->cand_corner, &c->site_key, &c->site_corner,
                           &c->site_xyz, &c->line_ptr, &c->line_ent, &c->g1, &c->g2, &c->stk, &c->id, &c->d2, &c->edge3,
                           &c->face3, &c->cube, &c->radius, &c->sk0, &c->sk1, &c->sv0, &c->sv1, &c->shist,

@@ -15,6 +15,16 @@ typedef unsigned int u32;
 typedef unsigned char u8;
 
 #define VC_MAX_WORKERS 16
+#define VC_MAX_PEERS 8
+
+// where a rank's site records go in the peer exchange (vc_peer.cu): rec[p] = start of THIS rank's
+// region inside rank p's receive buffer (keys at [0,cap), corners at [cap,2cap))
+struct VcPeerDst
+{
+    u64* rec[VC_MAX_PEERS] = {};
+    int world = 0;
+    u64 cap = 0;
+};
 
 struct DevBuf
 {
@@ -90,6 +100,13 @@ struct vc_ctx
     DevBuf cl_ptr, cl_ent, gsites; // int32 offsets, int32 site ids per cell, double3 sites
     int cl_dim[3] = {0, 0, 0};
     double cl_org[3] = {0, 0, 0}, cl_h = 1.0;
+    // peer exchange of the site records (vc_peer.cu): receive buffer of this rank, mapped buffers of the others
+    int peer_world = 0, peer_rank = -1;
+    int64_t peer_cap = 0;
+    u64 peer_seq = 0;
+    bool peer_posted = false, peer_ipc = false;
+    void* peer_base[VC_MAX_PEERS] = {};
+    DevBuf peer_rx, peer_all; // own receive buffer; gathered (keys | corners) of all ranks
     std::string err;
     bool profiling = false;
     std::vector<KStat> stats;
@@ -147,6 +164,8 @@ static inline bool vc_is_device_ptr(const void* p)
 // ---- stage functions (vc_stages.cu / vc_sites.cu / vc_edt.cu / vc_measures.cu) -------------------
 int st_classify(vc_ctx* c);
 int st_detect_sites(vc_ctx* c);
+int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter);
+void vc_peer_release(vc_ctx* c);
 int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key);
 int st_closest_lattice(vc_ctx* c);
 int st_measures(vc_ctx* c, bool want_radius);

@@ -1,0 +1,288 @@
+// vc_peer.cu -- the one exchange of the multi-GPU path, written over peer memory.
+//
+// Every rank (one process per GPU, one z-slab each) needs the UNION of the boundary-sample records
+// (first-encounter key, corner) of all slabs, because site ids are ranks in the global x-major scan
+// order (src/surfacing.cpp:240-285).  Instead of "detect -> count -> host -> all-gather -> host", the
+// detection kernel itself stores each record into the receive buffer of every rank over NVLink
+// (k_detect_sites<2>, vc_sites.cu), then one warp posts (sequence number, count) into every rank's
+// header with a system-scope release store.  A rank collects by spinning (acquire loads, bounded) on
+// its OWN header lines until all ranks have posted the current sequence number, packs the regions
+// into one contiguous record list and runs the same sort every other rank runs.  One host
+// synchronisation per exchange (the total count sizes the sort launches); no collective library on
+// the data path -- torch.distributed only carries the 64-byte IPC handles once, at set-up.
+//
+// Receive buffer of a rank (u64 units), double-buffered on the parity of the sequence number so a
+// fast rank's next exchange cannot overwrite what a slow rank is still packing:
+//     header  [2][VC_MAX_PEERS][8]      line (parity, source): [0] = sequence, [1] = record count
+//     records [2][world][2 * cap]       region (parity, source): keys[cap] | corners[cap]
+// A rank may start exchange k+2 only after collecting k+1, i.e. after every rank posted k+1, which
+// each does after packing k (stream order): two buffers are enough.
+#include <cstring>
+
+#include "vc_internal.h"
+
+#define PEER_HDR_U64 (2 * VC_MAX_PEERS * 8)
+#define PEER_SPIN_LIMIT (4000000000ll) // clock64 ticks (~2 s): a missing rank becomes an error, not a hang
+
+static size_t peer_rx_u64(int world, int64_t cap) { return (size_t)PEER_HDR_U64 + 2ull * world * 2ull * (size_t)cap; }
+static __host__ __device__ inline size_t peer_hdr_off(int parity, int src) { return ((size_t)parity * VC_MAX_PEERS + src) * 8; }
+static inline size_t peer_rec_off(int world, int64_t cap, int parity, int src)
+{
+    return (size_t)PEER_HDR_U64 + ((size_t)parity * world + src) * 2ull * (size_t)cap;
+}
+
+struct VcPeerHdr
+{
+    u64* line[VC_MAX_PEERS]; // header line (parity, my rank) inside rank p's receive buffer
+};
+
+// one warp: lane p tells rank p how many records this rank wrote (after they are visible system-wide)
+__global__ void k_peer_post(VcPeerHdr hdr, int world, const u64* __restrict__ counter, u64 seq)
+{
+    const int p = threadIdx.x;
+    if (p >= world)
+        return;
+    const u64 n = *counter;
+    __threadfence_system();
+    u64* line = hdr.line[p];
+    line[1] = n;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(line), "l"(seq) : "memory");
+}
+
+// one warp: lane p waits for rank p's post of `seq` in MY header, then the warp turns the counts into
+// offsets.  res[0] = total, res[1] = status (0 ok, 1 timeout, 2 a region overflowed), off[p] = start of p.
+__global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, u64 cap, u64* __restrict__ off,
+                            u64* __restrict__ res)
+{
+    const int p = threadIdx.x;
+    u64 n = 0;
+    int bad = 0;
+    if (p < world)
+    {
+        const u64* line = my_hdr + p * 8;
+        const long long t0 = clock64();
+        for (;;)
+        {
+            u64 s;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(line) : "memory");
+            if (s == seq)
+                break;
+            if (clock64() - t0 > PEER_SPIN_LIMIT)
+            {
+                bad = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        if (!bad)
+        {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(n) : "l"(line + 1) : "memory");
+            if (n > cap)
+                bad = 2;
+        }
+    }
+    u64 incl = bad ? 0 : n;
+    const u64 mine = incl;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (p >= o)
+            incl += t;
+    }
+    int worst = bad;
+    for (int o = 16; o; o >>= 1)
+        worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (p < world)
+        off[p] = incl - mine;
+    if (p == world - 1)
+    {
+        off[world] = incl;
+        res[0] = incl;
+        res[1] = (u64)worst;
+    }
+}
+
+// records of all regions -> one contiguous list: out[0 .. total) keys, out[total_cap ..) corners
+__global__ void __launch_bounds__(256)
+    k_peer_pack(const u64* __restrict__ rec, int world, u64 cap, const u64* __restrict__ off, u64* __restrict__ keys,
+                u64* __restrict__ corners)
+{
+    const int p = blockIdx.y;
+    const u64 n = off[p + 1] - off[p];
+    const u64* src = rec + (size_t)p * 2ull * cap;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    {
+        keys[off[p] + i] = __ldcg(src + i); // L2 is where the peers' stores land; never a stale L1 line
+        corners[off[p] + i] = __ldcg(src + cap + i);
+    }
+}
+
+void vc_peer_release(vc_ctx* c)
+{
+    if (c->peer_ipc)
+        for (int p = 0; p < c->peer_world; ++p)
+            if (p != c->peer_rank && c->peer_base[p])
+                cudaIpcCloseMemHandle(c->peer_base[p]);
+    for (int p = 0; p < VC_MAX_PEERS; ++p)
+        c->peer_base[p] = nullptr;
+    c->peer_rx.release();
+    c->peer_all.release();
+    c->peer_world = 0;
+    c->peer_rank = -1;
+    c->peer_cap = 0;
+    c->peer_ipc = c->peer_posted = false;
+    cudaGetLastError();
+}
+
+extern "C"
+{
+    int vc_peer_create(vc_ctx* c, int world, int rank, int64_t cap, void* handle_out)
+    {
+        if (!c || world < 1 || world > VC_MAX_PEERS || rank < 0 || rank >= world || cap < 1)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        vc_peer_release(c);
+        const size_t bytes = peer_rx_u64(world, cap) * 8;
+        VC_CUDA(c, c->peer_rx.ensure(bytes));
+        VC_CUDA(c, cudaMemset(c->peer_rx.p, 0, bytes)); // sequence numbers start at 0; the first exchange posts 1
+        VC_CUDA(c, c->peer_all.ensure((size_t)world * 2ull * (size_t)cap * 8));
+        c->peer_world = world;
+        c->peer_rank = rank;
+        c->peer_cap = cap;
+        c->peer_seq = 0;
+        c->peer_base[rank] = c->peer_rx.p;
+        if (handle_out)
+        {
+            cudaIpcMemHandle_t h;
+            VC_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_rx.p));
+            static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+            memcpy(handle_out, &h, sizeof(h));
+        }
+        return VC_OK;
+    }
+
+    int vc_peer_open(vc_ctx* c, const void* handles)
+    {
+        if (!c || !handles || c->peer_world < 1)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        for (int p = 0; p < c->peer_world; ++p)
+        {
+            if (p == c->peer_rank)
+                continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + (size_t)p * 64, 64);
+            void* base = nullptr;
+            VC_CUDA(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_base[p] = base;
+        }
+        c->peer_ipc = true;
+        return VC_OK;
+    }
+
+    int vc_peer_open_ptrs(vc_ctx* c, void* const* bases)
+    {
+        if (!c || !bases || c->peer_world < 1)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        for (int p = 0; p < c->peer_world; ++p)
+        {
+            if (p == c->peer_rank)
+                continue;
+            if (!bases[p])
+                return vc_fail(c, VC_ERR_INVALID, "vc_peer_open_ptrs: null receive buffer");
+            cudaPointerAttributes a;
+            VC_CUDA(c, cudaPointerGetAttributes(&a, bases[p]));
+            if (a.device != c->device)
+            {
+                cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return vc_fail(c, VC_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+                cudaGetLastError();
+            }
+            c->peer_base[p] = bases[p];
+        }
+        c->peer_ipc = false;
+        return VC_OK;
+    }
+
+    void* vc_peer_buffer(vc_ctx* c) { return c ? c->peer_rx.p : nullptr; }
+
+    int vc_peer_close(vc_ctx* c)
+    {
+        if (!c)
+            return VC_ERR_INVALID;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        vc_peer_release(c);
+        return VC_OK;
+    }
+
+    int vc_sites_post_peers(vc_ctx* c)
+    {
+        if (!c)
+            return VC_ERR_INVALID;
+        if (c->peer_world < 1)
+            return vc_fail(c, VC_ERR_STATE, "vc_sites_post_peers: no peer group (vc_peer_create / vc_peer_open)");
+        for (int p = 0; p < c->peer_world; ++p)
+            if (!c->peer_base[p])
+                return vc_fail(c, VC_ERR_STATE, "vc_sites_post_peers: a peer's receive buffer is not mapped");
+        if (c->peer_posted)
+            return vc_fail(c, VC_ERR_STATE, "vc_sites_post_peers: the previous exchange was not collected");
+        VC_CUDA(c, cudaSetDevice(c->device));
+        const u64 seq = c->peer_seq + 1;
+        const int parity = (int)(seq & 1);
+        VcPeerDst dst;
+        VcPeerHdr hdr;
+        dst.world = c->peer_world;
+        dst.cap = (u64)c->peer_cap;
+        for (int p = 0; p < c->peer_world; ++p)
+        {
+            u64* base = (u64*)c->peer_base[p];
+            dst.rec[p] = base + peer_rec_off(c->peer_world, c->peer_cap, parity, c->peer_rank);
+            hdr.line[p] = base + peer_hdr_off(parity, c->peer_rank);
+        }
+        u64* counter = c->scratch.as<u64>() + 2;
+        VC_TRY(st_detect_sites_to_peers(c, dst, counter));
+        VC_LAUNCH(c, "peer_post", k_peer_post, 1, 32, 0, hdr, c->peer_world, counter, seq);
+        VC_CUDA(c, cudaGetLastError());
+        c->peer_seq = seq;
+        c->peer_posted = true;
+        return VC_OK;
+    }
+
+    int vc_sites_collect_peers(vc_ctx* c, int64_t* n_all)
+    {
+        if (!c)
+            return VC_ERR_INVALID;
+        if (!c->peer_posted)
+            return vc_fail(c, VC_ERR_STATE, "vc_sites_collect_peers: nothing posted");
+        VC_CUDA(c, cudaSetDevice(c->device));
+        c->peer_posted = false;
+        const int world = c->peer_world;
+        const int parity = (int)(c->peer_seq & 1);
+        u64* base = (u64*)c->peer_rx.p;
+        u64* off = c->scratch.as<u64>() + 4; // world + 1 offsets, then res[2]
+        u64* res = off + VC_MAX_PEERS + 1;
+        VC_LAUNCH(c, "peer_wait", k_peer_wait, 1, 32, 0, base + peer_hdr_off(parity, 0), world, c->peer_seq,
+                  (u64)c->peer_cap, off, res);
+        u64* keys = c->peer_all.as<u64>();
+        u64* corners = keys + (size_t)world * (size_t)c->peer_cap;
+        unsigned bx = vc_blocks((size_t)c->peer_cap, 256);
+        bx = bx > 1024u ? 1024u : bx;
+        VC_LAUNCH(c, "peer_pack", k_peer_pack, dim3(bx, world), 256, 0, base + peer_rec_off(world, c->peer_cap, parity, 0), world,
+                  (u64)c->peer_cap, off, keys, corners);
+        u64* h = (u64*)c->pinned;
+        VC_CUDA(c, cudaMemcpyAsync(h, res, 16, cudaMemcpyDeviceToHost, c->stream));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (h[1] == 1)
+            return vc_fail(c, VC_ERR_STATE, "vc_sites_collect_peers: timed out waiting for a rank of the slab group");
+        if (h[1] == 2)
+            return vc_fail(c, VC_ERR_NOMEM, "vc_sites_collect_peers: a rank produced more site records than the capacity given "
+                                            "to vc_peer_create");
+        const int64_t n = (int64_t)h[0];
+        if (n_all)
+            *n_all = n;
+        return st_finalize_sites(c, keys, corners, n, true);
+    }
+}

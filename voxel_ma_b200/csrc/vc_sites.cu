@@ -183,10 +183,14 @@ int st_upload_f64_zfast(vc_ctx* c, const double* vol)
 // Warp-aggregated append; the order of the appended records does not matter because the keys are
 // unique and sorted afterwards.
 // =============================================================================================
-template <bool EMIT>
+// MODE 0: count only.  MODE 1: append (key, corner) records to keys[] / corners[].  MODE 2: append every
+// record to the receive region of EVERY rank of the slab group (vc_peer.cu): plain 8-byte stores
+// into peer memory over NVLink, no count pass -- a region has a fixed capacity and the counter tells
+// the receivers afterwards how many records (or that it overflowed).
+template <int MODE>
 __global__ void __launch_bounds__(256)
     k_detect_sites(const u32* __restrict__ bits, int wr, int nx, int ny, int nz, int zlo, int czb, int cze,
-                   u64* __restrict__ keys, u64* __restrict__ corners, u64* __restrict__ counter)
+                   u64* __restrict__ keys, u64* __restrict__ corners, u64* __restrict__ counter, VcPeerDst peers)
 {
     const int CY = ny + 1;
     const size_t total = (size_t)wr * CY * (size_t)(cze - czb);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256)
     if (lane == 31)
         base = atomicAdd(counter, (u64)warp_total);
     base = __shfl_sync(0xffffffffu, base, 31);
-    if (!EMIT)
+    if (MODE == 0)
         return;
     u64 pos = base + (u64)(incl - cnt);
     while (site)
@@ -256,10 +260,26 @@ __global__ void __launch_bounds__(256)
             const u32 rin = (rows_in >> k) & 1u;
             inb |= ((cx >= 1 ? rin : 0u) << k) | ((cx < nx ? rin : 0u) << (4 + k));
         }
-        keys[pos] = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
-        corners[pos] = vc_pack_corner(cx, cy, cz);
+        const u64 key = vc_site_key(occ, inb, cx, cy, cz, ny, nz), corner = vc_pack_corner(cx, cy, cz);
+        if (MODE == 1)
+        {
+            keys[pos] = key;
+            corners[pos] = corner;
+        }
+        else if (pos < peers.cap)
+        {
+#pragma unroll
+            for (int p = 0; p < VC_MAX_PEERS; ++p)
+                if (p < peers.world)
+                {
+                    peers.rec[p][pos] = key;
+                    peers.rec[p][peers.cap + pos] = corner;
+                }
+        }
         ++pos;
     }
+    if (MODE == 2)
+        __threadfence_system(); // the records are in the peers' memory before the count is posted (vc_peer.cu)
 }
 
 int st_detect_sites(vc_ctx* c)
@@ -275,8 +295,8 @@ int st_detect_sites(vc_ctx* c)
     u64* counter = c->scratch.as<u64>();
     VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
     unsigned blocks = vc_blocks(total, 256);
-    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<false>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny, c->nz,
-              c->zlo, czb, cze, nullptr, nullptr, counter);
+    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<0>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny, c->nz,
+              c->zlo, czb, cze, nullptr, nullptr, counter, VcPeerDst());
     u64 n = 0;
     VC_CUDA(c, cudaMemcpyAsync(&n, counter, 8, cudaMemcpyDeviceToHost, c->stream));
     VC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -286,10 +306,28 @@ int st_detect_sites(vc_ctx* c)
     if (n)
     {
         VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
-        VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<true>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
-                  c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter);
+        VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<1>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
+                  c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter, VcPeerDst());
         VC_CUDA(c, cudaGetLastError());
     }
+    return VC_OK;
+}
+
+// Site detection of this slab's corner planes written straight into every rank's receive region
+// (one pass: the regions have a fixed capacity, so nothing has to be counted first).  `counter`
+// (device, zeroed here) ends up holding the number of records this rank produced.
+int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter)
+{
+    if (!c->have_inside)
+        return vc_fail(c, VC_ERR_STATE, "site extraction needs vc_classify_grid first");
+    int czb = c->z0, cze = (c->z1 == c->nz) ? c->nz + 1 : c->z1;
+    if (c->zlo > (czb > 0 ? czb - 1 : 0) || c->zhi < (cze - 1 < c->nz ? cze : c->nz))
+        return vc_fail(c, VC_ERR_STATE, "resident voxel planes do not cover the slab's corner planes");
+    size_t total = (size_t)c->wr * (c->ny + 1) * (size_t)(cze - czb);
+    VC_CUDA(c, cudaMemsetAsync(counter, 0, 8, c->stream));
+    VC_LAUNCH(c, "detect_sites_emit_peers", k_detect_sites<2>, vc_blocks(total, 256), 256, 0, c->bits.as<u32>(), c->wr, c->nx,
+              c->ny, c->nz, c->zlo, czb, cze, nullptr, nullptr, counter, dst);
+    VC_CUDA(c, cudaGetLastError());
     return VC_OK;
 }
 

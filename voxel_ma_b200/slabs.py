@@ -56,6 +56,30 @@ def exchange_site_records(keys, corners, group=None):
     return all_keys.contiguous(), all_corners.contiguous()
 
 
+class PeerExchange:
+    """The same exchange over peer memory (csrc/vc_peer.cu): set up once per slab group, then
+    `exchange()` per step = vc_sites_post_peers + vc_sites_collect_peers, no collective call and one
+    host synchronisation.  torch.distributed only carries the 64-byte CUDA IPC handles here."""
+
+    def __init__(self, ctx, cap: int, group=None):
+        import torch.distributed as dist
+
+        self.ctx = ctx
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = ctx.peer_create(world, rank, int(cap))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        ctx.peer_open(handles)
+        dist.barrier(group=group)  # every receive buffer is zeroed and mapped before the first post
+
+    def exchange(self) -> int:
+        self.ctx.sites_post_peers()
+        return self.ctx.sites_collect_peers()
+
+    def close(self):
+        self.ctx.peer_close()
+
+
 def unpack_corners(corners_u64: np.ndarray) -> np.ndarray:
     """corner record cx | cy<<21 | cz<<42  ->  int32 (n,3)."""
     c = np.asarray(corners_u64, np.uint64)
