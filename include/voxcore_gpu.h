@@ -222,6 +222,36 @@ void* vc_device_ptr(vc_ctx* ctx, int which);
 int vc_run_dense_host(vc_ctx* ctx, const float* vol, uint8_t* inside, int32_t* id, uint32_t* d2x4,
                       float* edge3, float* face3, float* cube, float* radius, int64_t* nsites);
 
+/* ---- compact product: one record per INSIDE grid vertex ------------------------------------------
+ * All the reference keeps of this front end lives on inside elements: Voronoi vertices tagged
+ * outside are dropped on load (src/voroinfo.cpp:128-139) and a cell with an outside vertex is
+ * invalid, measure 0 (include/voroinfo_imp.h:26-34, src/voroinfo.cpp:1460-1461,1513-1514) -- on the
+ * dense grid all 7 measures anchored at an outside vertex are 0 by definition.  The compact product
+ * is the occupancy bit rows plus, for the inside vertices in ascending linear index
+ * v = x + nx*(y + ny*(z - z0)):  vert[i] = v, id[i], d2x4[i], lambda7[k*cap + i] (k = edge +x,+y,+z,
+ * face xy,xz,yz, cube), radius[i] -- the same values as the dense planes at v.  44 B per inside
+ * vertex cross the bus instead of 41 B per grid vertex.
+ *   vc_compact_count    inside vertices of the owned planes (needs vc_classify_grid)
+ *   vc_compact_records  gathers the records from the dense planes (needs vc_run_dense /
+ *                       vc_closest_and_measures); outputs host or device, nullable; cap >= count
+ *   vc_run_dense_host_compact  host volume in (float32 [z][y][x]), compact product out, all copies
+ *                       inside the call: upload classified chunk by chunk as it lands, records of a
+ *                       z chunk copied back while the next chunk computes.  inside_bits (nullable):
+ *                       uint32 [nz*ny][nx/32+1], bit x&31 of word x>>5.  id_dense / d2x4_dense
+ *                       (nullable): the full planes as well.  cap < count -> VC_ERR_NOMEM with the
+ *                       count in *n_inside.
+ *   vc_set_compact_mode how vc_run_dense_host_compact obtains the records: 1 = dense measure planes,
+ *                       then gathered; 2 = computed directly per inside vertex (the 8 dense float
+ *                       planes are then NOT produced by that call: vc_download of them fails with
+ *                       VC_ERR_STATE); 0 = automatic (2 when at most 1/8 of the vertices are inside).
+ *                       Same values either way. */
+int vc_set_compact_mode(vc_ctx* ctx, int mode);
+int vc_compact_count(vc_ctx* ctx, int64_t* n_inside);
+int vc_compact_records(vc_ctx* ctx, int64_t cap, uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius);
+int vc_run_dense_host_compact(vc_ctx* ctx, const float* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
+                              uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
+                              uint32_t* d2x4_dense, int64_t* nsites);
+
 /* ---- instrumentation --------------------------------------------------------------------------------
  * The reference's only instrumentation is struct timer around stages (include/commondefs.h:110-168);
  * here every kernel launch can be bracketed by CUDA events on the ctx stream. */

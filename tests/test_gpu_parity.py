@@ -104,6 +104,81 @@ def test_run_dense_host_matches(ctx):
     assert np.array_equal(e, oe) and np.array_equal(f, of) and np.array_equal(c, oc) and np.array_equal(r, orad)
 
 
+def _check_compact(vol, n, nsites, bits, vert, ids, d2, lam, rad):
+    """compact records == the oracle's dense planes at the inside vertices, in ascending linear order"""
+    nz, ny, nx = vol.shape
+    o_inside = ob.classify_grid(vol)
+    o_sites = ob.extract_sites(o_inside)
+    o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz) if len(o_sites) else (np.full(vol.shape, -1, np.int32), None)
+    where = np.flatnonzero(o_inside.ravel()).astype(np.uint32)
+    assert n == len(where) and nsites == len(o_sites)
+    assert np.array_equal(vert[:n], where)
+    if bits is not None:
+        wr = nx // 32 + 1
+        unpacked = np.unpackbits(bits.reshape(nz, ny, wr).view(np.uint8), axis=-1, bitorder="little")[:, :, :nx]
+        assert np.array_equal(unpacked, o_inside)
+    if n == 0 or len(o_sites) == 0:
+        return
+    oe, of, oc, orad = ob.cell_measures_grid(o_sites, o_ids, o_inside, nx, ny, nz)
+    assert np.array_equal(ids[:n], o_ids.ravel()[where]) and np.array_equal(d2[:n], o_d2.ravel()[where])
+    planes = [oe[0], oe[1], oe[2], of[0], of[1], of[2], oc]
+    for k, pl in enumerate(planes):
+        assert np.array_equal(lam[k, :n], pl.ravel()[where]), f"lambda plane {k}"
+    assert np.array_equal(rad[:n], orad.ravel()[where])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_compact_records_bit_exact(ctx, name):
+    vol = CASES[name]
+    nz, ny, nx = vol.shape
+    ctx.set_grid(nx, ny, nz)
+    ctx.upload_volume(vol)
+    ns = ctx.run_dense()
+    vert, ids, d2, lam, rad = ctx.compact_records()
+    _check_compact(vol, len(vert), ns, None, vert, ids, d2, lam, rad)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("fam,n,workers,zchunk", [("torus", 56, 8, 0), ("twist", 40, 3, 5), ("assembly", 33, 0, 0), ("sphere", 64, 4, 7)])
+def test_run_dense_host_compact_matches(ctx, fam, n, workers, zchunk, mode):
+    """host volume in, compact product out (upload classified chunk by chunk, records copied back per z chunk);
+    mode 1 = dense measure planes + gather, mode 2 = records computed directly per inside vertex"""
+    vol = synth.make(fam, n)
+    nz, ny, nx = vol.shape
+    ctx.set_grid(nx, ny, nz)
+    ctx.set_pipeline(workers, zchunk)
+    ctx.set_compact_mode(mode)
+    with pytest.raises(api.VoxcoreError, match="capacity"):
+        ctx.run_dense_host_compact(vol, 1, vert=np.empty(1, np.uint32))
+    cap = int((vol > 0).sum()) + 17
+    bits = np.empty((nz * ny, nx // 32 + 1), np.uint32)
+    vert, ids, d2 = np.empty(cap, np.uint32), np.empty(cap, np.int32), np.empty(cap, np.uint32)
+    lam, rad = np.empty((7, cap), np.float32), np.empty(cap, np.float32)
+    idd, d2d = np.empty(vol.shape, np.int32), np.empty(vol.shape, np.uint32)
+    for _ in range(2):  # twice: buffers reused
+        n_in, ns = ctx.run_dense_host_compact(vol, cap, bits, vert, ids, d2, lam, rad, idd, d2d)
+        _check_compact(vol, n_in, ns, bits, vert, ids, d2, lam, rad)
+        o_sites = ob.extract_sites(ob.classify_grid(vol))
+        o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
+        assert np.array_equal(idd, o_ids) and np.array_equal(d2d, o_d2)
+    if mode == 2:  # the dense float planes were not produced by that call, and the ABI says so
+        with pytest.raises(api.VoxcoreError, match="not computed"):
+            ctx.download(api.ARR_CUBE)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_run_dense_host_compact_direct_records_on_edge_cases(ctx, name):
+    vol = CASES[name]
+    nz, ny, nx = vol.shape
+    ctx.set_grid(nx, ny, nz)
+    ctx.set_compact_mode(2)
+    cap = int(ob.classify_grid(vol).sum()) + 1
+    vert, ids, d2 = np.empty(cap, np.uint32), np.empty(cap, np.int32), np.empty(cap, np.uint32)
+    lam, rad = np.empty((7, cap), np.float32), np.empty(cap, np.float32)
+    n_in, ns = ctx.run_dense_host_compact(np.ascontiguousarray(vol, np.float32), cap, None, vert, ids, d2, lam, rad)
+    _check_compact(vol, n_in, ns, None, vert, ids, d2, lam, rad)
+
+
 def test_f64_zfast_upload(ctx):
     vol = synth.sphere(24)
     nz, ny, nx = vol.shape

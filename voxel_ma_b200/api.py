@@ -26,7 +26,8 @@ SYMBOLS = [
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
     "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
-    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_profile_enable", "vc_profile_reset",
+    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
+    "vc_run_dense_host_compact", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
 
@@ -84,6 +85,10 @@ def load_library(path: str | None = None):
     lib.vc_peer_close.argtypes = [vp]
     lib.vc_sites_post_peers.argtypes = [vp]
     lib.vc_sites_collect_peers.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_set_compact_mode.argtypes = [vp, i32]
+    lib.vc_compact_count.argtypes = [vp, C.POINTER(i64)]
+    lib.vc_compact_records.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.vc_run_dense_host_compact.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
     lib.vc_closest_grid.argtypes = [vp, vp, vp]
     lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
     lib.vc_radius_search.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
@@ -394,6 +399,33 @@ class Context:
         self._ck(self.lib.vc_run_dense_host(self.h, _ptr(vol), _ptr(inside), _ptr(ids), _ptr(d2x4), _ptr(edge3),
                                             _ptr(face3), _ptr(cube), _ptr(radius), C.byref(n)))
         return n.value
+
+    # ---- compact product: records of the inside vertices (csrc/vc_compact.cu)
+    def set_compact_mode(self, mode: int) -> None:
+        """0 automatic, 1 dense planes + gather, 2 records computed directly (vc_run_dense_host_compact)"""
+        self._ck(self.lib.vc_set_compact_mode(self.h, mode))
+
+    def compact_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vc_compact_count(self.h, C.byref(n)))
+        return n.value
+
+    def compact_records(self):
+        """(vert u32[n], id i32[n], d2x4 u32[n], lambda7 f32[7][n], radius f32[n]) of the inside vertices"""
+        n = self.compact_count()
+        vert, ids, d2 = np.empty(n, np.uint32), np.empty(n, np.int32), np.empty(n, np.uint32)
+        lam, rad = np.empty((7, n), np.float32), np.empty(n, np.float32)
+        self._ck(self.lib.vc_compact_records(self.h, n, _ptr(vert), _ptr(ids), _ptr(d2), _ptr(lam), _ptr(rad)))
+        return vert, ids, d2, lam, rad
+
+    def run_dense_host_compact(self, vol, cap, inside_bits=None, vert=None, ids=None, d2x4=None, lambda7=None, radius=None,
+                               id_dense=None, d2x4_dense=None):
+        """-> (n_inside, n_sites).  lambda7 must be laid out [7][cap]."""
+        n, ns = C.c_int64(), C.c_int64()
+        self._ck(self.lib.vc_run_dense_host_compact(self.h, _ptr(vol), _ptr(inside_bits), cap, C.byref(n), _ptr(vert), _ptr(ids),
+                                                    _ptr(d2x4), _ptr(lambda7), _ptr(radius), _ptr(id_dense), _ptr(d2x4_dense),
+                                                    C.byref(ns)))
+        return n.value, ns.value
 
     def synchronize(self):
         self._ck(self.lib.vc_synchronize(self.h))

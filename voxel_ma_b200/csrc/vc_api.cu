@@ -108,7 +108,7 @@ extern "C"
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaHostAlloc(&c->pinned, 4096, cudaHostAllocDefault) != cudaSuccess || c->scratch.ensure(256) != cudaSuccess)
+            cudaHostAlloc(&c->pinned, 32768, cudaHostAllocDefault) != cudaSuccess || c->scratch.ensure(256) != cudaSuccess)
         {
             vc_ctx_destroy(c);
             return VC_ERR_CUDA;
@@ -147,7 +147,8 @@ extern "C"
         DevBuf* bufs[] = {&c->vol, &c->inside, &c->bits, &c->cand_key, &c->cand_corner, &c->site_key, &c->site_corner,
                           &c->site_xyz, &c->line_ptr, &c->line_ent, &c->g1, &c->g2, &c->stk, &c->id, &c->d2, &c->edge3,
                           &c->face3, &c->cube, &c->radius, &c->sk0, &c->sk1, &c->sv0, &c->sv1, &c->shist,
-                          &c->scratch, &c->cl_ptr, &c->cl_ent, &c->gsites};
+                          &c->scratch, &c->cl_ptr, &c->cl_ent, &c->gsites, &c->rowpre, &c->cvert, &c->cid, &c->cd2, &c->clam,
+                          &c->crad};
         for (auto b : bufs)
             b->release();
         if (c->pinned)

@@ -305,7 +305,9 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         return vc_fail(c, VC_ERR_STATE, "measures need vc_classify_grid");
     if (c->zhi < c->zc)
         return vc_fail(c, VC_ERR_STATE, "inside flags do not cover the halo plane");
-    VC_TRY(measures_alloc(c, want_radius));
+    const bool dense_measures = !c->skip_dense_measures;
+    if (dense_measures)
+        VC_TRY(measures_alloc(c, want_radius));
     if (nw)
     {
         VC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
@@ -320,8 +322,10 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         c->cur = nw ? c->workers[k % nw] : c->stream;
         status = edt_range(c, zb, zh, k, zchunk + 1);
         const int me = ze < c->z1 ? ze : c->z1;
-        if (status == VC_OK && zb < me)
+        if (status == VC_OK && zb < me && dense_measures)
             status = measures_range(c, zb, me, want_radius);
+        if (status == VC_OK && zb < me && c->chunk_hook)
+            status = c->chunk_hook(zb, me); // e.g. compaction + device-to-host copy of this chunk's records
     }
     c->cur = c->stream;
     if (nw)
@@ -333,6 +337,7 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
     if (status != VC_OK)
         return status;
     VC_CUDA(c, cudaGetLastError());
-    c->have_closest = c->have_measures = true;
+    c->have_closest = true;
+    c->have_measures = dense_measures;
     return VC_OK;
 }

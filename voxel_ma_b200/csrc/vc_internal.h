@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -107,6 +108,13 @@ struct vc_ctx
     bool peer_posted = false, peer_ipc = false;
     void* peer_base[VC_MAX_PEERS] = {};
     DevBuf peer_rx, peer_all; // own receive buffer; gathered (keys | corners) of all ranks
+    // compact product (vc_compact.cu): exclusive prefix of the inside count per bit row of the owned planes,
+    // records of the inside vertices; chunk_hook runs after the measures of each z chunk of the pipeline
+    DevBuf rowpre, cvert, cid, cd2, clam, crad;
+    int64_t ninside = -1, ccap = 0;
+    std::function<int(int, int)> chunk_hook;
+    int compact_mode = 0;             // 0 automatic, 1 dense planes + gather, 2 records computed directly
+    bool skip_dense_measures = false; // set by vc_run_dense_host_compact while its records are computed directly
     std::string err;
     bool profiling = false;
     std::vector<KStat> stats;
@@ -163,6 +171,10 @@ static inline bool vc_is_device_ptr(const void* p)
 
 // ---- stage functions (vc_stages.cu / vc_sites.cu / vc_edt.cu / vc_measures.cu) -------------------
 int st_classify(vc_ctx* c);
+bool st_classify_chunkable(const vc_ctx* c);
+int st_classify_begin(vc_ctx* c);
+int st_classify_planes(vc_ctx* c, int za, int zb);
+int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len);
 int st_detect_sites(vc_ctx* c);
 int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter);
 void vc_peer_release(vc_ctx* c);

@@ -109,30 +109,51 @@ __global__ void k_classify_f64_zfast(const double* __restrict__ vol, u8* __restr
     }
 }
 
-int st_classify(vc_ctx* c)
+// Classification in two steps so that a host-to-device upload can be classified plane chunk by
+// plane chunk while later chunks are still on the wire (vc_compact.cu): st_classify_begin sizes the
+// buffers and clears the pad word of every bit row, st_classify_planes handles voxel planes
+// [za, zb) of the resident range on stream c->cur.
+bool st_classify_chunkable(const vc_ctx* c) { return (c->nx & 31) == 0 || (((size_t)c->nx * c->ny) & 3) == 0; }
+
+int st_classify_begin(vc_ctx* c)
 {
     if (!c->have_vol)
         return vc_fail(c, VC_ERR_STATE, "vc_classify_grid: no volume uploaded");
     const size_t nrows = (size_t)c->ny * (size_t)(c->zhi - c->zlo);
-    size_t n = (size_t)c->nx * nrows;
-    VC_CUDA(c, c->inside.ensure(n + 16));
+    VC_CUDA(c, c->inside.ensure((size_t)c->nx * nrows + 16));
+    c->wr = c->nx / 32 + 1;
+    VC_CUDA(c, c->bits.ensure(nrows * (size_t)c->wr * 4 + 16));
+    if ((c->nx & 31) == 0)
+        VC_CUDA(c, cudaMemsetAsync(c->bits.p, 0, nrows * (size_t)c->wr * 4, c->cur)); // the pad word of every row
+    return VC_OK;
+}
+
+int st_classify_planes(vc_ctx* c, int za, int zb)
+{
+    const size_t nrows = (size_t)c->ny * (size_t)(zb - za), row0 = (size_t)c->ny * (size_t)(za - c->zlo);
+    const size_t n = (size_t)c->nx * nrows, off = (size_t)c->nx * row0;
+    if (n == 0)
+        return VC_OK;
     size_t want = (n / 4 + 255) / 256 + 1, cap = (size_t)c->sm_count * 16;
     unsigned blocks = (unsigned)(want < cap ? want : cap);
     if ((c->nx & 31) == 0)
-    {
-        c->wr = c->nx / 32 + 1;
-        VC_CUDA(c, c->bits.ensure(nrows * (size_t)c->wr * 4 + 16));
-        VC_CUDA(c, cudaMemsetAsync(c->bits.p, 0, nrows * (size_t)c->wr * 4, c->stream)); // the pad word of every row
-        VC_LAUNCH(c, "classify_f32", k_classify_f32<true>, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(),
-                  c->bits.as<u32>(), n, c->nx / 32, c->wr);
-    }
+        VC_LAUNCH(c, "classify_f32", k_classify_f32<true>, blocks, 256, 0, c->vol.as<float>() + off, c->inside.as<u8>() + off,
+                  c->bits.as<u32>() + row0 * (size_t)c->wr, n, c->nx / 32, c->wr);
     else
-    {
-        VC_LAUNCH(c, "classify_f32", k_classify_f32<false>, blocks, 256, 0, c->vol.as<float>(), c->inside.as<u8>(),
+    { // (a plane range that does not start on a 16-byte boundary must be the whole resident range: st_classify_chunkable)
+        VC_LAUNCH(c, "classify_f32", k_classify_f32<false>, blocks, 256, 0, c->vol.as<float>() + off, c->inside.as<u8>() + off,
                   (u32*)nullptr, n, 0, 0);
-        VC_TRY(pack_bits(c));
+        VC_LAUNCH(c, "pack_bits", k_pack_bits, vc_blocks(nrows * (size_t)c->wr, 256), 256, 0, c->inside.as<u8>() + off,
+                  c->bits.as<u32>() + row0 * (size_t)c->wr, nrows, c->nx, c->wr);
     }
     VC_CUDA(c, cudaGetLastError());
+    return VC_OK;
+}
+
+int st_classify(vc_ctx* c)
+{
+    VC_TRY(st_classify_begin(c));
+    VC_TRY(st_classify_planes(c, c->zlo, c->zhi));
     c->have_inside = true;
     c->have_sites = c->have_closest = c->have_measures = false;
     return VC_OK;
@@ -475,6 +496,14 @@ __global__ void __launch_bounds__(256)
 
 // note: the histogram kernel tiles by (item, thread) and the scatter by (warp, item, lane); both
 // cover exactly [tile*RS_TILE, (tile+1)*RS_TILE), which is all the per-tile counts depend on.
+// exclusive prefix of len u32 values in place (device), on stream c->cur
+int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len)
+{
+    VC_LAUNCH(c, "scan_u32", k_rs_scan, 1, 1024, 0, a, len);
+    VC_CUDA(c, cudaGetLastError());
+    return VC_OK;
+}
+
 int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io)
 {
     if (n <= 1)
