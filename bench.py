@@ -460,10 +460,19 @@ def run_ours(args):
             "edt_pass_y": 8 * (nx * (ny + 1) + nx * ny) * planes_c,
         }
         roof = None
+        traffic, traffic_src, sm_pct = None, None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's whole-grid launch, from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("workload") == f"{fam}{nx}x{ny}x{nz}" and dom in tj["kernels"]:
+                k = tj["kernels"][dom]
+                traffic = (k["dram_read_gb"] + k["dram_write_gb"]) * 1e9
+                traffic_src, sm_pct = tj["source"], k.get("sm_throughput_pct")
+        except Exception:
+            pass
         if dom in unit_bytes:
             ach = unit_bytes[dom] / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": unit_bytes[dom],
+                    "traffic": traffic, "traffic_source": traffic_src, "sm_throughput_pct_ncu": sm_pct, "peak_source": peak_src, "bytes_per_launch": unit_bytes[dom],
                     "ms_per_launch": kern[dom]["ms_per_launch"], "share_of_step": kern[dom]["ms_per_step"] / (ms_prof / steps)}
         pipe_ach = BYTES_PIPELINE * nv_local / (ms_per_step * 1e-3) / 1e9
         line = {
