@@ -144,6 +144,13 @@ int vc_closest_grid(vc_ctx* ctx, int32_t* id_out, uint32_t* d2x4_out);
  * d2 = squared distance in double. Host pointers. */
 int vc_closest_points(vc_ctx* ctx, const double* q, int64_t n, int32_t* id, double* d2);
 
+/* float32 form: drop-in for trimesh::KDtree::closest_to_pt(p, maxdist2)
+ * (3rdparty/trimesh2/libsrc/KDtree.cc:252-292,523-545; call site estimateRadiiField,
+ * src/exporters.cpp:629-636).  Distances are the tree's own: sqr(x0-q0) + sqr(x1-q1) + sqr(x2-q2) in
+ * float32; only sites with d2 < max_d2 qualify (max_d2 <= 0 or inf: no limit); ties -> lowest id.
+ * q = n x 3 floats; id = -1 and d2 = -1 when nothing qualifies.  Host pointers; d2 nullable. */
+int vc_closest_points_f32(vc_ctx* ctx, const float* q, int64_t n, float max_d2, int32_t* id, float* d2);
+
 /* Fixed-radius query: drop-in for annkFRSearch(q, sqRad, k, idx, dd, 0.0)
  * (3rdparty/ann/src/kd_fix_rad_search.cpp:58-189; call sites src/voxelapps.cpp:346,353).  sq_rad[i] is
  * the SQUARED radius, inclusive (dist <= sqRad, :172).  count[i] = number of sites in range (what the

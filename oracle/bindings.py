@@ -68,6 +68,7 @@ def oracle():
         lib.orc_extract_sites.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
         lib.orc_extract_sites.restype = C.c_int64
         lib.orc_closest_points.argtypes = [_f64p, C.c_int64, C.c_int, _f64p, C.c_int64, _i32p, C.c_void_p]
+        lib.orc_closest_points_f32.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_float, _i32p, C.c_void_p]
         lib.orc_closest_grid.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _i32p, C.c_void_p, C.c_void_p]
         lib.orc_face_lambda.argtypes = [_f32p, _i32p, C.c_int64, _f32p]
@@ -103,6 +104,7 @@ def ref():
             f.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _i32p, _f64p]
         lib.ref_ann_kd_fr_search.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _f64p, C.c_int,
                                              _i32p, C.c_void_p, C.c_void_p]
+        lib.ref_kdtree_closest.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_float, _i32p, _f32p]
         lib.ref_lambda_for_face.argtypes = [_f32p, _f32p, C.c_int64, _f32p]
         lib.ref_pipeline_run.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_int]
         lib.ref_pipeline_run.restype = C.c_void_p
@@ -210,6 +212,16 @@ def closest_points(sites: np.ndarray, q: np.ndarray):
     return idx, d2
 
 
+def closest_points_f32(pts, q, max_d2=0.0):
+    """float32 nearest point (trimesh KDtree semantics): (idx, d2), -1 where nothing within max_d2"""
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float32)
+    oracle().orc_closest_points_f32(p, len(p), q, len(q), float(max_d2), idx, d2.ctypes.data)
+    return idx, d2
+
+
 def closest_grid(sites_xyz: np.ndarray, nx, ny, nz, z0=0, z1=None, want_d2=False):
     z1 = nz if z1 is None else z1
     s = np.ascontiguousarray(sites_xyz, np.float32)
@@ -312,6 +324,16 @@ def ref_ann_fr(sites, q, sq_rad):
     if kmax:
         ref().ref_ann_kd_fr_search(s, len(s), 3, q, len(q), r, kmax, cnt, idx.ctypes.data, d2.ctypes.data)
     return cnt, idx, d2
+
+
+def ref_kdtree_closest(pts, q, max_d2):
+    """the real trimesh::KDtree::closest_to_pt + trimesh::dist, as estimateRadiiField uses them: (idx, dist)"""
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
+    idx = np.empty(len(q), np.int32)
+    d = np.empty(len(q), np.float32)
+    ref().ref_kdtree_closest(p, len(p), q, len(q), float(max_d2), idx, d)
+    return idx, d
 
 
 def ref_lambda(a, b):

@@ -177,6 +177,43 @@ void orc_closest_points(const double* sites, int64_t ns, int dim, const double* 
     }
 }
 
+/* float32 nearest point: what trimesh::KDtree::closest_to_pt(p, maxdist2) answers
+ * (3rdparty/trimesh2/libsrc/KDtree.cc:252-292 leaf test `myd2 < closest_d2`, :523-545 entry with
+ * closest_d2 = maxdist2; distance :28-33 = sqr(x0-y0) + sqr(x1-y1) + sqr(x2-y2) in float, x = tree
+ * point).  The caller (estimateRadiiField, src/exporters.cpp:629-636) only uses the DISTANCE of the
+ * returned point, so the tree's traversal-dependent choice among equidistant points does not show;
+ * this restatement reports the lowest index.  max_d2 <= 0 or inf: no limit.  idx = -1, d2 = -1 when
+ * no point has d2 < max_d2. */
+void orc_closest_points_f32(const float* pts, int64_t n, const float* q, int64_t nq, float max_d2, int32_t* idx, float* d2)
+{
+    const float lim = (max_d2 > 0.0f && max_d2 < INFINITY) ? max_d2 : INFINITY;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nq; ++i)
+    {
+        float best = lim;
+        int32_t bi = -1;
+        const float* y = q + 3 * (size_t)i;
+        for (int64_t s = 0; s < n; ++s)
+        {
+            const float* x = pts + 3 * (size_t)s;
+            float t = x[0] - y[0];
+            float d = t * t;
+            t = x[1] - y[1];
+            d = d + t * t;
+            t = x[2] - y[2];
+            d = d + t * t;
+            if (d < best)
+            {
+                best = d;
+                bi = (int32_t)s;
+            }
+        }
+        idx[i] = bi;
+        if (d2)
+            d2[i] = bi < 0 ? -1.0f : best;
+    }
+}
+
 /* Dense query set: one query per grid vertex (integer lattice point) against float32 sites widened
  * to double exactly as the reference widens them for ANN (src/voroinfo.cpp:336-341).  Outputs the
  * id and 4*d2 as an exact integer (sites on the half-integer lattice make 4*d2 integral; for

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#include <trimesh/KDtree.h>
 #include <unistd.h>
 #include <chrono>
 
@@ -175,6 +176,21 @@ extern "C"
         }
         annDeallocPts(pa);
         annClose();
+    }
+
+    // f-2: trimesh::KDtree::closest_to_pt as estimateRadiiField calls it (src/exporters.cpp:626-637):
+    // idx = index of the returned point (-1 when NULL), d = trimesh::dist(point(closest), v)
+    void ref_kdtree_closest(const float* pts, int64_t n, const float* q, int64_t nq, float maxdist2, int32_t* idx,
+                            float* d)
+    {
+        Stopwatch sw;
+        trimesh::KDtree tree(pts, (size_t)n);
+        for (int64_t i = 0; i < nq; ++i)
+        {
+            const float* c = tree.closest_to_pt(q + 3 * i, maxdist2);
+            idx[i] = c ? (int32_t)((c - pts) / 3) : -1;
+            d[i] = c ? trimesh::dist(trimesh::point(c), trimesh::point(q + 3 * i)) : -1.0f;
+        }
     }
 
     // a5 contract: ANNbruteForce::annkSearch (3rdparty/ann/src/brute.cpp:56-82): (d2, lowest id)

@@ -155,6 +155,40 @@ def cli_sphere64():
             f.write(f"sha256 {k} {h}\n")
 
 
+def cli_more():
+    """SURVEY 8f-2 / 8f-3 through the unmodified CLI: `-md=r` (estimateRadiiField, trimesh KDtree) and
+    `-dofuncmap=bt3` (assignScalarToSites -> match_voro_with_medialcurve, ANN) on the inputs of
+    tests/cli_cases.py; output file hashes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cli_cases
+    out = ["# unmodified reference CLI on the inputs of tests/cli_cases.py"]
+    with tempfile.TemporaryDirectory() as d:
+        args = cli_cases.write_radii_case(d, ob.ref_extract_sites(synth.torus(48)))
+        subprocess.run([ob.REF_CLI, *args], cwd=d, capture_output=True, text=True, check=True)
+        out.append("case radii " + " ".join(args))
+        out.append("sha256 radii.txt " + hashlib.sha256(open(os.path.join(d, "radii.txt"), "rb").read()).hexdigest())
+    with tempfile.TemporaryDirectory() as d:
+        args = cli_cases.write_funcmap_case(d)
+        subprocess.check_call(["cp", os.path.join(ROOT, "oracle/_ref/cycle8.txt"), d])
+        subprocess.run([ob.REF_CLI, *args], cwd=d, capture_output=True, text=True, check=True)
+        out.append("case funcmap " + " ".join(args))
+        for f in ("out.bt3.msure", "dbg_mc_smoothed.msure", "out.ply", "out.r"):
+            out.append(f"sha256 {f} " + hashlib.sha256(open(os.path.join(d, f), "rb").read()).hexdigest())
+    open(os.path.join(OUT, "cli_more.txt"), "w").write("\n".join(out) + "\n")
+
+
+def kdtree_f32():
+    """trimesh::KDtree::closest_to_pt + trimesh::dist exactly as estimateRadiiField uses them (8f-2), from the
+    REAL tree: lattice boundary points of torus(32), float queries, lattice queries (exact ties) and far
+    queries, with a finite search limit (some queries find nothing)."""
+    pts = ob.ref_extract_sites(synth.torus(32))
+    rng = np.random.default_rng(515)
+    q = np.concatenate([rng.uniform(0, 31, (1500, 3)), rng.integers(0, 32, (700, 3)), rng.uniform(-20, 50, (300, 3))]).astype(np.float32)
+    lim = np.float32(150.0)
+    idx, dist = ob.ref_kdtree_closest(pts, q, lim)
+    np.savez_compressed(os.path.join(OUT, "kdtree_f32.npz"), pts=pts, q=q, max_d2=lim, found=(idx >= 0), dist=dist)
+
+
 if __name__ == "__main__":
     if not (os.path.isdir(REF) and ob.have_ref()):
         sys.exit("needs /root/reference and oracle/_ref (make -f oracle/Makefile.ref)")
@@ -164,4 +198,6 @@ if __name__ == "__main__":
     pipeline()
     fr_search()
     cli_sphere64()
+    cli_more()
+    kdtree_f32()
     print("golden fixtures written to", OUT)

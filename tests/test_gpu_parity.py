@@ -482,3 +482,30 @@ def test_radius_search_general_sites_and_edge_radii(ctx):
     assert np.array_equal(cnt, ocnt) and (cnt[:5] >= 1).all() and (cnt[10:20] == 0).all() and (cnt[20:24] == 5000).all()
     assert np.array_equal(idx, oidx) and np.array_equal(d2, od2)
     assert np.array_equal(ctx.radius_search(q, sq, fetch=False), ocnt)
+
+
+# ---- float32 nearest point (trimesh::KDtree::closest_to_pt drop-in) ---------------------
+def test_closest_points_f32_golden(ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kdtree_f32.npz"))
+    ctx.set_grid(32, 32, 32)
+    ctx.set_sites(g["pts"])  # lattice sites
+    idx, d2 = ctx.closest_points_f32(g["q"], float(g["max_d2"]))
+    assert np.array_equal(idx >= 0, g["found"])
+    dist = np.where(idx >= 0, np.sqrt(np.maximum(d2, 0), dtype=np.float32), np.float32(-1))
+    assert np.array_equal(dist, g["dist"]), "radii must equal the real KD-tree's bit for bit"
+    oi, od2 = ob.closest_points_f32(g["pts"], g["q"], float(g["max_d2"]))
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od2)  # ties -> lowest id, as the restatement
+
+
+def test_closest_points_f32_general_sites(ctx):
+    rng = np.random.default_rng(31)
+    pts = rng.uniform(0, 50, (20000, 3)).astype(np.float32)
+    q = np.concatenate([rng.uniform(-10, 60, (6000, 3)), pts[:50]]).astype(np.float32)
+    ctx.set_grid(50, 50, 50)
+    ctx.set_sites(pts)
+    for lim in (0.0, 3.0, float("inf")):
+        idx, d2 = ctx.closest_points_f32(q, lim)
+        oi, od2 = ob.closest_points_f32(pts, q, lim)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od2)
+    assert (d2[-50:] == 0).all()

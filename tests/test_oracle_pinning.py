@@ -132,3 +132,23 @@ def test_fixed_radius_search_vs_live_reference():
         o = np.lexsort((ri[i, : rc[i]], rd[i, : rc[i]]))
         assert np.array_equal(idx[off[i]:off[i + 1]], ri[i, : rc[i]][o])
         assert np.array_equal(d2[off[i]:off[i + 1]], rd[i, : rc[i]][o])
+
+
+def test_kdtree_f32_golden():
+    """8f-2: the float32 nearest-point restatement against the real trimesh::KDtree (golden from the reference)"""
+    g = np.load(os.path.join(G, "kdtree_f32.npz"))
+    idx, d2 = ob.closest_points_f32(g["pts"], g["q"], float(g["max_d2"]))
+    assert np.array_equal(idx >= 0, g["found"]) and 0 < g["found"].sum() < len(g["found"])
+    dist = np.where(idx >= 0, np.sqrt(np.maximum(d2, 0), dtype=np.float32), np.float32(-1))
+    assert np.array_equal(dist, g["dist"])
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built")
+def test_kdtree_f32_vs_live_reference():
+    rng = np.random.default_rng(99)
+    pts = rng.uniform(0, 30, (4000, 3)).astype(np.float32)
+    q = rng.uniform(-3, 33, (3000, 3)).astype(np.float32)
+    ridx, rdist = ob.ref_kdtree_closest(pts, q, 40.0)
+    idx, d2 = ob.closest_points_f32(pts, q, 40.0)
+    assert np.array_equal(ridx >= 0, idx >= 0)
+    assert np.array_equal(rdist, np.where(idx >= 0, np.sqrt(np.maximum(d2, 0), dtype=np.float32), np.float32(-1)))

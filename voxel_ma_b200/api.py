@@ -25,7 +25,7 @@ SYMBOLS = [
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
     "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
-    "vc_closest_points", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
+    "vc_closest_points", "vc_closest_points_f32", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
     "vc_run_dense_host_compact", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
@@ -91,6 +91,7 @@ def load_library(path: str | None = None):
     lib.vc_run_dense_host_compact.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
     lib.vc_closest_grid.argtypes = [vp, vp, vp]
     lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
+    lib.vc_closest_points_f32.argtypes = [vp, vp, i64, C.c_float, vp, vp]
     lib.vc_radius_search.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.vc_cell_measures_grid.argtypes = [vp, vp, vp, vp, vp]
     lib.vc_face_lambda.argtypes = [vp, vp, i64, vp]
@@ -290,6 +291,14 @@ class Context:
         ids = np.empty(self.slab_shape, np.int32) if fetch else None
         d2 = np.empty(self.slab_shape, np.uint32) if fetch else None
         self._ck(self.lib.vc_closest_grid(self.h, _ptr(ids), _ptr(d2)))
+        return ids, d2
+
+    def closest_points_f32(self, q, max_d2=0.0):
+        """trimesh::KDtree::closest_to_pt for a batch: float32 distances, (id, d2); -1 where nothing within max_d2"""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
+        ids = np.empty(len(q), np.int32)
+        d2 = np.empty(len(q), np.float32)
+        self._ck(self.lib.vc_closest_points_f32(self.h, _ptr(q), len(q), float(max_d2), _ptr(ids), _ptr(d2)))
         return ids, d2
 
     def closest_points(self, q):

@@ -445,6 +445,14 @@ extern "C"
         return st_closest_points(c, q, n, id, d2);
     }
 
+    int vc_closest_points_f32(vc_ctx* c, const float* q, int64_t n, float max_d2, int32_t* id, float* d2)
+    {
+        if (!c || n < 0 || (n > 0 && (!q || !id)))
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        return st_closest_points_f32(c, q, n, max_d2, id, d2);
+    }
+
     int vc_cell_measures_grid(vc_ctx* c, float* edge3, float* face3, float* cube, float* radius)
     {
         if (!c)

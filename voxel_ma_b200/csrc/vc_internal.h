@@ -201,6 +201,7 @@ int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* 
 // general sites
 int st_build_cell_list(vc_ctx* c, const float* xyz_host, int64_t n);
 int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double* d2);
+int st_closest_points_f32(vc_ctx* c, const float* q, int64_t n, float max_d2, int32_t* id, float* d2);
 int st_closest_general_grid(vc_ctx* c);
 int st_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n, const int64_t* off, int32_t* count, int32_t* idx,
                      double* d2);

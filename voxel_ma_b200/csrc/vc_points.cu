@@ -10,6 +10,7 @@
 // site id (3rdparty/ann/src/brute.cpp:56-82 -- the kd-tree returns the same distance but an
 // order-dependent id).
 #include <cmath>
+#include <vector>
 
 #include "vc_internal.h"
 
@@ -87,12 +88,36 @@ __device__ __forceinline__ void scan_cell(const double* __restrict__ ps, const i
     }
 }
 
+// float32 variant: trimesh::KDtree's distance (3rdparty/trimesh2/libsrc/KDtree.cc:28-33), sqr(x0-y0) + sqr(x1-y1) +
+// sqr(x2-y2) in float with x = the tree point; sites and query are floats widened exactly, so the casts are lossless
+__device__ __forceinline__ void scan_cell_f32(const double* __restrict__ ps, const int* __restrict__ ent, int b, int e, double q0,
+                                              double q1, double q2, double& best, int& bid)
+{
+    const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2;
+    for (int k = b; k < e; ++k)
+    {
+        float t = __fsub_rn((float)ps[3 * k], f0);
+        float d = __fmul_rn(t, t);
+        t = __fsub_rn((float)ps[3 * k + 1], f1);
+        d = __fadd_rn(d, __fmul_rn(t, t));
+        t = __fsub_rn((float)ps[3 * k + 2], f2);
+        d = __fadd_rn(d, __fmul_rn(t, t));
+        int id = ent[k];
+        if ((double)d < best || ((double)d == best && id < bid))
+        {
+            best = (double)d;
+            bid = id;
+        }
+    }
+}
+
 // GRID = false: queries are q[3*i..]; GRID = true: query i is the grid vertex (x,y,z) of the slab.
-template <bool GRID>
+// F32 = true: float32 distances (see scan_cell_f32), only sites with d2 < max_d2 qualify.
+template <bool GRID, bool F32 = false>
 __global__ void __launch_bounds__(128)
     k_closest_points(const double* __restrict__ q, int64_t n, CellGrid g, const int* __restrict__ ptr,
                      const double* __restrict__ ps, const int* __restrict__ ent, int nx, int ny, int z0, int* __restrict__ id_out,
-                     double* __restrict__ d2_out, u32* __restrict__ d2x4_out)
+                     double* __restrict__ d2_out, u32* __restrict__ d2x4_out, double max_d2 = INFINITY)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -112,15 +137,24 @@ __global__ void __launch_bounds__(128)
         q2 = q[3 * i + 2];
     }
     const int c0 = cg_cell(g, q0, 0), c1 = cg_cell(g, q1, 1), c2 = cg_cell(g, q2, 2);
-    double best = INFINITY;
+    double best = max_d2;
     int bid = -1;
     const int rmax = max(g.dim[0], max(g.dim[1], g.dim[2]));
+    // a float32 distance is within a few 1e-7 (relative) of the exact one: stop only with that much room
+    const double slack = F32 ? (1.0 - 1e-5) : (1.0 - 1e-12);
+    auto scan = [&](int b, int e)
+    {
+        if (F32)
+            scan_cell_f32(ps, ent, b, e, q0, q1, q2, best, bid);
+        else
+            scan_cell(ps, ent, b, e, q0, q1, q2, best, bid);
+    };
     for (int r = 0; r <= rmax; ++r)
     {
         if (r > 0)
         {
             double lim = (double)(r - 1) * g.h; // every unvisited site is at least (r-1)*h away once ring r-1 is done
-            if (best < lim * lim * (1.0 - 1e-12))
+            if (best < lim * lim * slack)
                 break;
         }
         const int zl = c2 - r, zh = c2 + r, yl = c1 - r, yh = c1 + r, xl = c0 - r, xh = c0 + r;
@@ -135,14 +169,14 @@ __global__ void __launch_bounds__(128)
                 { // the whole x-run belongs to the ring: cells are consecutive in the list
                     int xa = max(xl, 0), xb = min(xh, g.dim[0] - 1);
                     if (xa <= xb)
-                        scan_cell(ps, ent, ptr[row + xa], ptr[row + xb + 1], q0, q1, q2, best, bid);
+                        scan(ptr[row + xa], ptr[row + xb + 1]);
                 }
                 else
                 {
                     if (xl >= 0)
-                        scan_cell(ps, ent, ptr[row + xl], ptr[row + xl + 1], q0, q1, q2, best, bid);
+                        scan(ptr[row + xl], ptr[row + xl + 1]);
                     if (xh < g.dim[0] && r > 0)
-                        scan_cell(ps, ent, ptr[row + xh], ptr[row + xh + 1], q0, q1, q2, best, bid);
+                        scan(ptr[row + xh], ptr[row + xh + 1]);
                 }
             }
         }
@@ -330,6 +364,50 @@ int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double
     dd.release();
     if (e != cudaSuccess)
         return vc_fail(c, VC_ERR_CUDA, "closest_points", e);
+    return VC_OK;
+}
+
+// float32 form: drop-in for trimesh::KDtree::closest_to_pt(p, maxdist2) (3rdparty/trimesh2/libsrc/KDtree.cc:252-292,
+// 523-545; call site src/exporters.cpp:629-636).  id = -1 / d2 = -1 when no site has d2 < max_d2.
+int st_closest_points_f32(vc_ctx* c, const float* q, int64_t n, float max_d2, int32_t* id, float* d2)
+{
+    if (!c->have_sites)
+        return vc_fail(c, VC_ERR_STATE, "vc_closest_points_f32 needs sites");
+    if (n == 0)
+        return VC_OK;
+    VC_TRY(ensure_cell_list(c));
+    std::vector<double> qd((size_t)n * 3);
+    for (size_t k = 0; k < qd.size(); ++k)
+        qd[k] = (double)q[k];
+    std::vector<double> dd((size_t)n);
+    DevBuf dq, did, ddv;
+    cudaError_t e = dq.ensure((size_t)n * 24);
+    if (e == cudaSuccess)
+        e = did.ensure((size_t)n * 4);
+    if (e == cudaSuccess)
+        e = ddv.ensure((size_t)n * 8);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dq.p, qd.data(), (size_t)n * 24, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+    {
+        const double lim = (max_d2 > 0.0f && max_d2 < INFINITY) ? (double)max_d2 : (double)INFINITY;
+        VC_LAUNCH(c, "closest_points_f32", (k_closest_points<false, true>), vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), n,
+                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), 0, 0, 0, did.as<int>(),
+                  ddv.as<double>(), (u32*)nullptr, lim);
+        e = cudaMemcpyAsync(id, did.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dd.data(), ddv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    dq.release();
+    did.release();
+    ddv.release();
+    if (e != cudaSuccess)
+        return vc_fail(c, VC_ERR_CUDA, "closest_points_f32", e);
+    if (d2)
+        for (int64_t i = 0; i < n; ++i)
+            d2[i] = id[i] < 0 ? -1.0f : (float)dd[(size_t)i];
     return VC_OK;
 }
 
