@@ -12,6 +12,9 @@
 // Order: ascending linear vertex index, fixed by an exclusive prefix over the popcounts of the
 // occupancy bit rows -- no atomics, so the record order is deterministic and a z chunk of the
 // pipeline owns one contiguous range of records that can start its copy as soon as the chunk is done.
+#include <cstdio>
+#include <cstdlib>
+
 #include "vc_internal.h"
 
 // inside count of every bit row of the owned planes; cnt[nrows] = 0 so the scan leaves the total there
@@ -369,6 +372,17 @@ extern "C"
         c->zhi = c->nz;
         c->have_vol = true;
         c->have_inside = c->have_sites = c->have_closest = c->have_measures = false;
+        const bool trace = getenv("VC_TRACE") != nullptr; // development aid: where the call's time goes
+        cudaEvent_t tev[6] = {};
+        auto mark = [&](int i, cudaStream_t st)
+        {
+            if (trace)
+            {
+                cudaEventCreate(&tev[i]);
+                cudaEventRecord(tev[i], st);
+            }
+        };
+        mark(0, c->s_h2d);
         VC_TRY(st_classify_begin(c));
         // upload in plane chunks on the copy stream; a chunk is classified as soon as it has landed
         const bool chunked = st_classify_chunkable(c);
@@ -390,6 +404,8 @@ extern "C"
         if (!chunked)
             VC_TRY(st_classify_planes(c, 0, c->nz));
         c->have_inside = true;
+        mark(1, c->s_h2d);
+        mark(2, c->stream);
         auto after_main = [&](cudaStream_t s) -> int
         { // s waits for everything queued on the main stream so far
             VC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -416,6 +432,7 @@ extern "C"
             return vc_fail(c, VC_ERR_NOMEM, "vc_run_dense_host_compact: capacity below the inside count (returned in n_inside)");
         }
         VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+        mark(3, c->stream);
         VC_TRY(compact_alloc(c, n, true));
         std::vector<u32> Ph(P, P + c->nz + 1); // the pinned scratch is reused by later stages
         // few inside vertices: their measures go straight into the records and the 8 dense float planes are
@@ -442,7 +459,19 @@ extern "C"
         hook_status = st_closest_measures_pipelined(c, true);
         c->chunk_hook = nullptr;
         c->skip_dense_measures = false;
+        mark(4, c->stream);
+        mark(5, c->s_d2h);
         cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
+        if (trace && e1 == cudaSuccess && e2 == cudaSuccess)
+        {
+            float t[6] = {0};
+            for (int i = 1; i < 6; ++i)
+                cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+            fprintf(stderr, "[vc trace] upload done %.3f | classified %.3f | sites numbered %.3f | transform+records %.3f | "
+                            "copied back %.3f ms\n", t[1], t[2], t[3], t[4], t[5]);
+            for (int i = 0; i < 6; ++i)
+                cudaEventDestroy(tev[i]);
+        }
         VC_TRY(hook_status);
         VC_CUDA(c, e1);
         VC_CUDA(c, e2);

@@ -95,6 +95,7 @@ struct vc_ctx
     DevBuf stk; // envelope stacks of the transform passes (packed u64 per line and depth)
     // sort scratch
     DevBuf sk0, sk1, sv0, sv1, shist;
+    int coop_sort = -1; // blocks of the single-launch cooperative radix sort that fit the device (0: launch per phase)
     DevBuf scratch; // small device scratch (counters)
     void* pinned = nullptr; // small pinned host scratch
     // general (non-lattice) sites: uniform cell list

@@ -162,10 +162,101 @@ __global__ void __launch_bounds__(32 * CM_TH, 3)
         return r;
     };
 
-    u32 nib_cur = nibble(x, y, zs);
-    park_plane(0, zs, nib_cur);
     const bool row_live = y < ny && x < nx;
     size_t o = (size_t)x + (size_t)nx * (size_t)y + plane * (size_t)(zs - z0);
+    // Streaming path.  When no vertex of the block's tile (halo row and column included) is inside on any of its
+    // planes, every lambda it owns is 0 and nothing has to be parked or synchronised: the block only streams the
+    // radius (from the d2x4 plane) and the zeros.  Thin solids in a large grid take this path almost everywhere.
+    {
+        u32 any = 0;
+        for (int z = zs; z <= ze; ++z)
+        {
+            any |= nibble(x, y, z);
+            if (ty == 0)
+                any |= nibble(x, y0 + CM_TH, z);
+            if (tx == 31)
+            {
+                const int xx = x0 + CM_TW;
+                for (int row = ty; row <= CM_TH; row += (ty == 0 ? CM_TH : CM_TH + 1))
+                { // row ty, and the corner row for ty == 0
+                    const int yy = y0 + row;
+                    if (xx < nx && yy < ny && z < zc)
+                        any |= (__ldg(bits + ((size_t)(z - zlo) * ny + yy) * (size_t)wr + (xx >> 5)) >> (xx & 31)) & 1u;
+                }
+            }
+        }
+        if (!__syncthreads_or((int)any))
+        {
+            if (!row_live)
+                return;
+            const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int z = zs; z < ze; ++z, o += plane)
+            {
+                float lr[CM_VX] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (radius)
+                {
+                    u32 q[CM_VX];
+                    if (VEC)
+                    {
+                        uint4 v = __ldcs(reinterpret_cast<const uint4*>(d2x4 + o));
+                        q[0] = v.x, q[1] = v.y, q[2] = v.z, q[3] = v.w;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < CM_VX; ++k)
+                            q[k] = (x + k < nx) ? __ldcs(d2x4 + o + k) : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < CM_VX; ++k)
+                    {
+                        if (radius_from_d2 && q[k] < (1u << 24))
+                            lr[k] = __fsqrt_rn(__fmul_rn((float)q[k], 0.25f));
+                        else if (x + k < nx)
+                        {
+                            int sid = __ldg(id + o + k);
+                            if (sid >= 0)
+                            {
+                                float4 sp = __ldg(site + sid);
+                                lr[k] = __fsqrt_rn(vc_dist2f(sp.x, sp.y, sp.z, (float)(x + k), (float)y, (float)z));
+                            }
+                        }
+                    }
+                }
+                auto put0 = [&](float* base, const float* v)
+                {
+                    if (VEC)
+                        __stcs(reinterpret_cast<float4*>(base + o), v ? make_float4(v[0], v[1], v[2], v[3]) : zero4);
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < CM_VX; ++k)
+                            if (x + k < nx)
+                                __stcs(base + o + k, v ? v[k] : 0.0f);
+                    }
+                };
+                if (edge3)
+                {
+                    put0(edge3, nullptr);
+                    put0(edge3 + nv, nullptr);
+                    put0(edge3 + 2 * nv, nullptr);
+                }
+                if (face3)
+                {
+                    put0(face3, nullptr);
+                    put0(face3 + nv, nullptr);
+                    put0(face3 + 2 * nv, nullptr);
+                }
+                if (cube)
+                    put0(cube, nullptr);
+                if (radius)
+                    put0(radius, lr);
+            }
+            return;
+        }
+    }
+    u32 nib_cur = nibble(x, y, zs);
+    park_plane(0, zs, nib_cur);
     for (int z = zs; z < ze; ++z, o += plane)
     {
         const int bufa = (z - zs) % 3, bufb = (z - zs + 1) % 3;

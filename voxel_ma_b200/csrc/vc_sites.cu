@@ -4,7 +4,14 @@
 //
 // Replaces: SpaceConverter::get_occupancy_at_vox over all voxels (include/spaceinfo.h:122-129) and
 // Surfacer::extractBoundaryVts (src/surfacing.cpp:223-321).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "vc_internal.h"
+
+namespace cg = cooperative_groups;
 
 // =============================================================================================
 // K1  classify: inside <=> value > 0.0  (NaN, 0, -0 are outside).  5 B / voxel: one 128-bit load,
@@ -494,6 +501,156 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- all passes in ONE launch --------------------------------------------------------------------
+// The sort is small (10^5 .. 10^7 records) and made of dependent passes, so three launches per pass
+// (27 for the two sorts of a 1024^3 site set) cost more in launch gaps than in work.  This kernel is the
+// same algorithm -- same tiles, same per-tile counts, same stable ranking, hence the same result --
+// run by a persistent cooperative grid with grid-wide barriers between the phases of a pass:
+//   A  per-tile digit histograms                                   (blocks stride over tiles)
+//   B  exclusive scan of every digit's row of tile counts, in place  (one warp per digit) + digit totals
+//   C  digit bases from the 256 totals (every block, redundantly), then the scatter of its tiles
+__global__ void __launch_bounds__(256)
+    k_rs_sort_coop(u64* __restrict__ k0, u32* __restrict__ v0, u64* __restrict__ k1, u32* __restrict__ v1,
+                   u32* __restrict__ ghist, u32* __restrict__ dtot, int64_t n, int nbits, int ntiles)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u32 wcnt[8][256];
+    __shared__ u32 dbase[256];
+    __shared__ u32 wsum[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u64* kin = k0;
+    u32* vin = v0;
+    u64* kout = k1;
+    u32* vout = v1;
+    for (int shift = 0; shift < nbits; shift += 8)
+    {
+        // A
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        {
+            u32* h = &wcnt[0][0];
+            h[threadIdx.x] = 0;
+            __syncthreads();
+            const int64_t base = (int64_t)tile * RS_TILE;
+            for (int i = 0; i < RS_ITEMS; ++i)
+            {
+                int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
+                if (idx < n)
+                    atomicAdd(&h[(u32)(kin[idx] >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            ghist[(size_t)threadIdx.x * ntiles + tile] = h[threadIdx.x];
+            __syncthreads();
+        }
+        grid.sync();
+        // B
+        for (int d = blockIdx.x * 8 + warp; d < 256; d += gridDim.x * 8)
+        {
+            u32* row = ghist + (size_t)d * ntiles;
+            u32 carry = 0;
+            for (int t0 = 0; t0 < ntiles; t0 += 32)
+            {
+                const int t = t0 + lane;
+                const u32 v = t < ntiles ? row[t] : 0u;
+                u32 inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    u32 x = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += x;
+                }
+                if (t < ntiles)
+                    row[t] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0)
+                dtot[d] = carry;
+        }
+        grid.sync();
+        // C
+        {
+            const u32 v = dtot[threadIdx.x];
+            u32 inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                u32 x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += x;
+            }
+            if (lane == 31)
+                wsum[warp] = inc;
+            __syncthreads();
+            u32 before = 0;
+            for (int w = 0; w < warp; ++w)
+                before += wsum[w];
+            dbase[threadIdx.x] = before + inc - v;
+            __syncthreads();
+        }
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        {
+            for (int i = threadIdx.x; i < 8 * 256; i += 256)
+                (&wcnt[0][0])[i] = 0;
+            __syncthreads();
+            const int64_t base = (int64_t)tile * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+            u64 k[RS_ITEMS];
+            u32 rk[RS_ITEMS];
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; ++i)
+            {
+                int64_t idx = base + (int64_t)i * 32 + lane;
+                bool valid = idx < n;
+                k[i] = valid ? kin[idx] : 0ull;
+                u32 d = (u32)(k[i] >> shift) & 255u;
+                unsigned m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+                int leader = __ffs(m) - 1;
+                u32 old = 0;
+                if (valid && lane == leader)
+                {
+                    old = wcnt[warp][d];
+                    wcnt[warp][d] = old + __popc(m);
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rk[i] = old + __popc(m & ((1u << lane) - 1));
+                __syncwarp();
+            }
+            __syncthreads();
+            {
+                const int d = threadIdx.x;
+                u32 run = dbase[d] + ghist[(size_t)d * ntiles + tile];
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                {
+                    u32 cc = wcnt[w][d];
+                    wcnt[w][d] = run;
+                    run += cc;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; ++i)
+            {
+                int64_t idx = base + (int64_t)i * 32 + lane;
+                if (idx < n)
+                {
+                    u32 d = (u32)(k[i] >> shift) & 255u;
+                    u32 pos = wcnt[warp][d] + rk[i];
+                    kout[pos] = k[i];
+                    vout[pos] = vin[idx];
+                }
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        u64* tk = kin;
+        kin = kout;
+        kout = tk;
+        u32* tv = vin;
+        vin = vout;
+        vout = tv;
+    }
+}
+
 // note: the histogram kernel tiles by (item, thread) and the scatter by (warp, item, lane); both
 // cover exactly [tile*RS_TILE, (tile+1)*RS_TILE), which is all the per-tile counts depend on.
 // exclusive prefix of len u32 values in place (device), on stream c->cur
@@ -511,11 +668,41 @@ int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** va
     if (n >= (int64_t)1 << 31)
         return vc_fail(c, VC_ERR_UNSUPPORTED, "radix sort: more than 2^31 records");
     int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
-    VC_CUDA(c, c->shist.ensure((size_t)256 * ntiles * sizeof(u32)));
+    VC_CUDA(c, c->shist.ensure(((size_t)256 * ntiles + 256) * sizeof(u32)));
     u64* kin = *keys_io;
     u32* vin = *vals_io;
     u64* kout = (kin == c->sk0.as<u64>()) ? c->sk1.as<u64>() : c->sk0.as<u64>();
     u32* vout = (vin == c->sv0.as<u32>()) ? c->sv1.as<u32>() : c->sv0.as<u32>();
+    if (c->coop_sort < 0)
+    { // once per ctx: can a cooperative grid be launched here, and how many blocks fit
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rs_sort_coop, 256, 0) == cudaSuccess && per_sm > 0)
+            c->coop_sort = per_sm * c->sm_count;
+        else
+            c->coop_sort = 0;
+        if (const char* e = getenv("VC_SORT"))
+            if (!strcmp(e, "legacy"))
+                c->coop_sort = 0;
+        cudaGetLastError();
+    }
+    if (c->coop_sort > 0)
+    {
+        int grid = ntiles < c->coop_sort ? ntiles : c->coop_sort;
+        grid = grid < 32 ? (32 < c->coop_sort ? 32 : c->coop_sort) : grid; // phase B wants 256 warps' worth of rows covered quickly
+        u32* gh = c->shist.as<u32>();
+        u32* dtot = gh + (size_t)256 * ntiles;
+        int nb = nbits;
+        void* args[] = {&kin, &vin, &kout, &vout, &gh, &dtot, &n, &nb, &ntiles};
+        {
+            ProfScope ps(c, "radix_sort_coop");
+            VC_CUDA(c, cudaLaunchCooperativeKernel((void*)k_rs_sort_coop, dim3(grid), dim3(256), args, 0, c->cur));
+        }
+        const int passes = (nbits + 7) / 8;
+        *keys_io = (passes & 1) ? kout : kin;
+        *vals_io = (passes & 1) ? vout : vin;
+        return VC_OK;
+    }
     for (int shift = 0; shift < nbits; shift += 8)
     {
         VC_LAUNCH(c, "radix_hist", k_rs_hist, ntiles, 256, 0, kin, n, shift, c->shist.as<u32>(), ntiles);
