@@ -112,8 +112,12 @@ struct vc_stack_array
 };
 
 // emit(t, V, id): the winner at target t has 4*d^2-so-far V and site id `id` (both 0xFFFFFFFF: no candidate)
+// mask (nullable): this line's candidate bitmap, bit (j & 31) of mask[j >> 5]; a clear bit means candidate j is
+// known to be VC_INF and in[j*stride] is neither read nor prefetched (pass X: columns without sites, whose G1
+// entries pass Z never writes).  One word serves 32 candidates and the next one is requested a word ahead.
 template <class Stack, class Emit>
-VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt, Stack& stk, Emit emit)
+VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncand, int ntgt, Stack& stk, Emit emit,
+                            const uint32_t* __restrict__ mask = nullptr)
 {
     // two upper entries in registers: top (gt, pt, idt) and second (gs, ps, ids); a = gt - gs, b = pt - ps
     int q = -1, gt = 0, pt = 0, gs = 0, ps = 0, a = 0, b = 1;
@@ -154,15 +158,29 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
         ++q;
     };
     vc_u64 bankA[VC_PF], bankB[VC_PF];
+    // candidate bitmap words: mw covers the 32 candidates of the FETCH in hand (VC_PF divides 32), mw_next the
+    // following 32; without a mask every candidate is live
+    const int nmw = (ncand + 31) >> 5;
+    uint32_t mw = 0xFFFFFFFFu, mw_next = 0xFFFFFFFFu;
+    if (mask)
+    {
+        mw_next = nmw > 0 ? mask[0] : 0u;
+    }
 #define VC_FETCH(bank, j0)                                                                         \
+    if (mask && (((j0) & 31) == 0))                                                                \
+    {                                                                                              \
+        mw = mw_next;                                                                              \
+        mw_next = (((j0) >> 5) + 1 < nmw) ? mask[((j0) >> 5) + 1] : 0u;                             \
+    }                                                                                              \
     _Pragma("unroll") for (int k = 0; k < VC_PF; ++k)                                              \
     {                                                                                              \
-        bank[k] = ((j0) + k < ncand) ? VC_LOAD_STREAM(in + (long)((j0) + k) * stride) : (vc_u64)VC_INF; \
-        if (VC_PF_L2 > 0 && (j0) + k + VC_PF_L2 < ncand)                                           \
+        bank[k] = ((j0) + k < ncand && ((mw >> (((j0) + k) & 31)) & 1u)) ? VC_LOAD_STREAM(in + (long)((j0) + k) * stride) \
+                                                                       : (vc_u64)VC_INF;         \
+        if (VC_PF_L2 > 0 && !mask && (j0) + k + VC_PF_L2 < ncand)                                   \
             VC_PREFETCH_L2(in + (long)((j0) + k + VC_PF_L2) * stride);                             \
     }
 #define VC_CONSUME(bank, j0) _Pragma("unroll") for (int k = 0; k < VC_PF; ++k) push(bank[k], (j0) + k);
-    if (VC_PF_L2 > 0)
+    if (VC_PF_L2 > 0 && !mask)
         for (int j = 0; j < VC_PF_L2 && j < ncand; ++j)
             VC_PREFETCH_L2(in + (long)j * stride);
     VC_FETCH(bankA, 0)

@@ -34,11 +34,7 @@ __global__ void __launch_bounds__(256)
     const size_t plane = (size_t)nlines;
     u64* out = G1 + l + plane * (size_t)(zb - z0);
     if (first == last)
-    {
-        for (int vz = zb; vz < ze; ++vz, out += plane)
-            __stcs(out, (u64)VC_INF);
-        return;
-    }
+        return; // a column without sites: pass X knows from the column mask and never reads these entries
     int nxt = first; // index of the first entry with cz > vz
     u64 below = VC_INF, above = ent[first];
     for (int vz = zb; vz < ze; ++vz, out += plane)
@@ -145,7 +141,7 @@ template <bool TRANSPOSE>
 __global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANSPOSE ? XY_MINB_T : XY_MINB_D)
     k_pass_xy(const u64* __restrict__ in, u64* __restrict__ G2, int* __restrict__ id_out, u32* __restrict__ d2_out,
               u64* __restrict__ stack, long nlines_total, int lines_per_plane, long in_plane_stride, long in_stride,
-              int ncand, int ntgt)
+              int ncand, int ntgt, const u32* __restrict__ colmask)
 {
     constexpr int NTHR = TRANSPOSE ? XY_THREADS_T : XY_THREADS_D;
     __shared__ u64 tile[TRANSPOSE ? XY_THREADS_T / 32 : 1][TRANSPOSE ? 32 : 1][TRANSPOSE ? XY_TW + 1 : 1];
@@ -181,7 +177,8 @@ __global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANS
                                          *dst = tile[warp][r][col];
                                  __syncwarp();
                              }
-                         });
+                         },
+                         colmask ? colmask + (size_t)within * (size_t)((ncand + 31) >> 5) : nullptr);
     }
     else
     {
@@ -221,14 +218,15 @@ static void launch_passes(vc_ctx* c, int zb, int nplanes, u64* stack)
     {
         long nlines = (long)nplanes * CY;
         VC_LAUNCH(c, "edt_pass_x", k_pass_xy<true>, vc_blocks((size_t)nlines, XY_THREADS_T), XY_THREADS_T, 0, g1, g2,
-                  (int*)nullptr, (u32*)nullptr, stack, nlines, CY, (long)CX * CY, (long)CY, CX, c->nx);
+                  (int*)nullptr, (u32*)nullptr, stack, nlines, CY, (long)CX * CY, (long)CY, CX, c->nx,
+                  c->colmask.as<u32>());
     }
     // pass Y: lines (vz, vx)
     {
         long nlines = (long)nplanes * c->nx;
         VC_LAUNCH(c, "edt_pass_y", k_pass_xy<false>, vc_blocks((size_t)nlines, XY_THREADS_D), XY_THREADS_D, 0, g2,
                   (u64*)nullptr, c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, stack, nlines,
-                  c->nx, (long)CY * c->nx, (long)c->nx, CY, c->ny);
+                  c->nx, (long)CY * c->nx, (long)c->nx, CY, c->ny, (const u32*)nullptr);
     }
 }
 

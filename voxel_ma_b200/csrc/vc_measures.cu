@@ -168,21 +168,20 @@ __global__ void __launch_bounds__(32 * CM_TH, 3)
     // planes, every lambda it owns is 0 and nothing has to be parked or synchronised: the block only streams the
     // radius (from the d2x4 plane) and the zeros.  Thin solids in a large grid take this path almost everywhere.
     {
+        // the tile's occupancy words: planes zs..ze (ze = halo), rows y0..y0+CM_TH (halo row), words of x0..x0+CM_TW
+        // (halo column = bit 0 of the fifth word); spread over the block's threads so the loads are independent
         u32 any = 0;
-        for (int z = zs; z <= ze; ++z)
+        const int w0 = x0 >> 5, nwords = CM_TW / 32 + 1, per_plane = (CM_TH + 1) * nwords;
+        const int total = (ze - zs + 1) * per_plane;
+        for (int i = threadIdx.x; i < total; i += 32 * CM_TH)
         {
-            any |= nibble(x, y, z);
-            if (ty == 0)
-                any |= nibble(x, y0 + CM_TH, z);
-            if (tx == 31)
+            const int pz = i / per_plane, r = i - pz * per_plane;
+            const int row = r / nwords, w = r - row * nwords;
+            const int zz = zs + pz, yy = y0 + row, ww = w0 + w;
+            if (zz < zc && yy < ny && ww < wr)
             {
-                const int xx = x0 + CM_TW;
-                for (int row = ty; row <= CM_TH; row += (ty == 0 ? CM_TH : CM_TH + 1))
-                { // row ty, and the corner row for ty == 0
-                    const int yy = y0 + row;
-                    if (xx < nx && yy < ny && z < zc)
-                        any |= (__ldg(bits + ((size_t)(z - zlo) * ny + yy) * (size_t)wr + (xx >> 5)) >> (xx & 31)) & 1u;
-                }
+                const u32 word = __ldg(bits + ((size_t)(zz - zlo) * ny + yy) * (size_t)wr + ww);
+                any |= (w == nwords - 1) ? (word & 1u) : word;
             }
         }
         if (!__syncthreads_or((int)any))
@@ -190,6 +189,7 @@ __global__ void __launch_bounds__(32 * CM_TH, 3)
             if (!row_live)
                 return;
             const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 4
             for (int z = zs; z < ze; ++z, o += plane)
             {
                 float lr[CM_VX] = {0.0f, 0.0f, 0.0f, 0.0f};

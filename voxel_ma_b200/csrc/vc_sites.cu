@@ -782,6 +782,26 @@ __global__ void k_line_ptr(const u64* __restrict__ key2_sorted, int64_t n, int n
     line_ptr[l] = (int)lo;
 }
 
+// colmask[cy][w]: bit (cx & 31) of word w = cx >> 5 is set when z-line (cx,cy) holds at least one site
+__global__ void k_line_mask(const int* __restrict__ line_ptr, int CX, int CY, int nw, u32* __restrict__ mask)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CY * nw)
+        return;
+    const int cy = i / nw, w = i - cy * nw;
+    u32 word = 0;
+    for (int b = 0; b < 32; ++b)
+    {
+        const int cx = 32 * w + b;
+        if (cx < CX)
+        {
+            const int l = cx * CY + cy;
+            word |= (u32)(line_ptr[l + 1] > line_ptr[l]) << b;
+        }
+    }
+    mask[i] = word;
+}
+
 // number of adjacent equal keys in a sorted array (duplicate detection for external site sets)
 __global__ void k_count_dups(const u64* __restrict__ k, int64_t n, u64* counter)
 {
@@ -811,6 +831,7 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
     VC_CUDA(c, c->site_xyz.ensure((size_t)(n + 1) * 16));
     VC_CUDA(c, c->line_ent.ensure((size_t)(n + 1) * 8));
     VC_CUDA(c, c->line_ptr.ensure((size_t)(nlines + 2) * 4));
+    VC_CUDA(c, c->colmask.ensure((size_t)(c->ny + 1) * (size_t)((c->nx + 32) >> 5) * 4 + 16));
     VC_CUDA(c, c->sk0.ensure((size_t)(n + 1) * 8));
     VC_CUDA(c, c->sk1.ensure((size_t)(n + 1) * 8));
     VC_CUDA(c, c->sv0.ensure((size_t)(n + 1) * 4));
@@ -818,6 +839,7 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
     if (n == 0)
     {
         VC_CUDA(c, cudaMemsetAsync(c->line_ptr.p, 0, (size_t)(nlines + 2) * 4, c->stream));
+        VC_CUDA(c, cudaMemsetAsync(c->colmask.p, 0, (size_t)(c->ny + 1) * (size_t)((c->nx + 32) >> 5) * 4, c->stream));
         c->have_sites = true;
         c->have_closest = c->have_measures = false;
         return VC_OK;
@@ -845,6 +867,11 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
     VC_LAUNCH(c, "line_entries", k_line_entries, blocks, 256, 0, k2, v2, c->line_ent.as<u64>(), n, c->nz);
     VC_LAUNCH(c, "line_ptr", k_line_ptr, vc_blocks((size_t)nlines + 1, 256), 256, 0, k2, n, nlines, c->nz,
               c->line_ptr.as<int>());
+    {
+        const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
+        VC_LAUNCH(c, "line_mask", k_line_mask, vc_blocks((size_t)CY * nw, 256), 256, 0, c->line_ptr.as<int>(), CX, CY, nw,
+                  c->colmask.as<u32>());
+    }
     if (!sort_by_key)
     { // external set: duplicates on the lattice would need the lowest-id rule inside a list entry
         u64* counter = c->scratch.as<u64>();
