@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(256)
 //   A  per-tile digit histograms                                   (blocks stride over tiles)
 //   B  exclusive scan of every digit's row of tile counts, in place  (one warp per digit) + digit totals
 //   C  digit bases from the 256 totals (every block, redundantly), then the scatter of its tiles
-__global__ void __launch_bounds__(256)
+#define CS_ITEMS 8                 // keys per thread and tile in the cooperative kernel (24 registers of keys + ranks)
+#define CS_TILE (256 * CS_ITEMS)
+__global__ void __launch_bounds__(256, 4)
     k_rs_sort_coop(u64* __restrict__ k0, u32* __restrict__ v0, u64* __restrict__ k1, u32* __restrict__ v1,
                    u32* __restrict__ ghist, u32* __restrict__ dtot, int64_t n, int nbits, int ntiles)
 {
@@ -524,21 +526,38 @@ __global__ void __launch_bounds__(256)
     u32* vout = v1;
     for (int shift = 0; shift < nbits; shift += 8)
     {
-        // A
+        // A: per-tile digit counts.  Per-warp counting with match_any (the scatter's own ranking step) instead of
+        // shared-memory atomics: the high digits of nearly sorted keys are all equal inside a tile, which would
+        // serialise 2048 atomics on one address.
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         {
-            u32* h = &wcnt[0][0];
-            h[threadIdx.x] = 0;
+            for (int i = threadIdx.x; i < 8 * 256; i += 256)
+                (&wcnt[0][0])[i] = 0;
             __syncthreads();
-            const int64_t base = (int64_t)tile * RS_TILE;
-            for (int i = 0; i < RS_ITEMS; ++i)
+            const int64_t base = (int64_t)tile * CS_TILE + (int64_t)warp * (32 * CS_ITEMS);
+            u64 k[CS_ITEMS];
+#pragma unroll
+            for (int i = 0; i < CS_ITEMS; ++i)
             {
-                int64_t idx = base + (int64_t)i * 256 + threadIdx.x;
-                if (idx < n)
-                    atomicAdd(&h[(u32)(kin[idx] >> shift) & 255u], 1u);
+                int64_t idx = base + (int64_t)i * 32 + lane;
+                k[i] = idx < n ? kin[idx] : ~0ull;
+            }
+#pragma unroll
+            for (int i = 0; i < CS_ITEMS; ++i)
+            {
+                const bool valid = base + (int64_t)i * 32 + lane < n;
+                const u32 d = (u32)(k[i] >> shift) & 255u;
+                const unsigned m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+                if (valid && lane == __ffs(m) - 1)
+                    wcnt[warp][d] += __popc(m);
+                __syncwarp();
             }
             __syncthreads();
-            ghist[(size_t)threadIdx.x * ntiles + tile] = h[threadIdx.x];
+            u32 tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                tot += wcnt[w][threadIdx.x];
+            ghist[(size_t)threadIdx.x * ntiles + tile] = tot;
             __syncthreads();
         }
         grid.sync();
@@ -592,15 +611,21 @@ __global__ void __launch_bounds__(256)
             for (int i = threadIdx.x; i < 8 * 256; i += 256)
                 (&wcnt[0][0])[i] = 0;
             __syncthreads();
-            const int64_t base = (int64_t)tile * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
-            u64 k[RS_ITEMS];
-            u32 rk[RS_ITEMS];
+            const int64_t base = (int64_t)tile * CS_TILE + (int64_t)warp * (32 * CS_ITEMS);
+            u64 k[CS_ITEMS];
+            u32 rk[CS_ITEMS], val[CS_ITEMS];
 #pragma unroll
-            for (int i = 0; i < RS_ITEMS; ++i)
+            for (int i = 0; i < CS_ITEMS; ++i)
             {
                 int64_t idx = base + (int64_t)i * 32 + lane;
-                bool valid = idx < n;
+                const bool valid = idx < n;
                 k[i] = valid ? kin[idx] : 0ull;
+                val[i] = valid ? vin[idx] : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < CS_ITEMS; ++i)
+            {
+                const bool valid = base + (int64_t)i * 32 + lane < n;
                 u32 d = (u32)(k[i] >> shift) & 255u;
                 unsigned m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
                 int leader = __ffs(m) - 1;
@@ -628,15 +653,14 @@ __global__ void __launch_bounds__(256)
             }
             __syncthreads();
 #pragma unroll
-            for (int i = 0; i < RS_ITEMS; ++i)
+            for (int i = 0; i < CS_ITEMS; ++i)
             {
-                int64_t idx = base + (int64_t)i * 32 + lane;
-                if (idx < n)
+                if (base + (int64_t)i * 32 + lane < n)
                 {
                     u32 d = (u32)(k[i] >> shift) & 255u;
                     u32 pos = wcnt[warp][d] + rk[i];
                     kout[pos] = k[i];
-                    vout[pos] = vin[idx];
+                    vout[pos] = val[i];
                 }
             }
             __syncthreads();
@@ -688,12 +712,14 @@ int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** va
     }
     if (c->coop_sort > 0)
     {
-        int grid = ntiles < c->coop_sort ? ntiles : c->coop_sort;
-        grid = grid < 32 ? (32 < c->coop_sort ? 32 : c->coop_sort) : grid; // phase B wants 256 warps' worth of rows covered quickly
+        int ctiles = (int)((n + CS_TILE - 1) / CS_TILE);
+        VC_CUDA(c, c->shist.ensure(((size_t)256 * ctiles + 256) * sizeof(u32)));
+        int grid = ctiles < c->coop_sort ? ctiles : c->coop_sort;
+        grid = grid < 32 ? (32 < c->coop_sort ? 32 : c->coop_sort) : grid; // phase B: 256 digit rows, one warp each
         u32* gh = c->shist.as<u32>();
-        u32* dtot = gh + (size_t)256 * ntiles;
+        u32* dtot = gh + (size_t)256 * ctiles;
         int nb = nbits;
-        void* args[] = {&kin, &vin, &kout, &vout, &gh, &dtot, &n, &nb, &ntiles};
+        void* args[] = {&kin, &vin, &kout, &vout, &gh, &dtot, &n, &nb, &ctiles};
         {
             ProfScope ps(c, "radix_sort_coop");
             VC_CUDA(c, cudaLaunchCooperativeKernel((void*)k_rs_sort_coop, dim3(grid), dim3(256), args, 0, c->cur));

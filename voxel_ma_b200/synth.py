@@ -83,11 +83,17 @@ def twist(n: int = 512, z0=None, z1=None) -> np.ndarray:
     return np.broadcast_to(f, (f.shape[0], f.shape[1], f.shape[2])).astype(np.float32)
 
 
-def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None) -> np.ndarray:
+# SURVEY section 8d-4 fixes assembly1024 at 64 solids and S ~ 2-3e6 boundary samples; with radii drawn from
+# [0.03, 0.10] x side the 64 solids give 5.5e6, so the named workloads shrink every radius by this factor
+# (S ~ 2.5e6 at 1024^3: the same samples-per-vertex density as twist512).
+ASSEMBLY_RSCALE = 0.67
+
+
+def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None, rscale: float = 1.0) -> np.ndarray:
     """Union of `count` solids (spheres, tori, boxes) with centres / radii drawn from
     mt19937(seed).  ``n`` is a side length or an (nx, ny, nz) triple; solids are placed in the unit
-    cube and scaled per axis extent, sized by the smallest side.  Built solid by solid on each
-    solid's bounding box only, so a rank can generate just its own z-slab."""
+    cube and scaled per axis extent, sized by the smallest side; `rscale` scales every radius.  Built
+    solid by solid on each solid's bounding box only, so a rank can generate just its own z-slab."""
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
     m = min(nx, ny, nz)
     rng = np.random.Generator(np.random.MT19937(seed))  # mt19937; seeded deterministically
@@ -98,7 +104,7 @@ def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None) -> np
     for _ in range(count):
         kind = int(rng.integers(0, 3))
         c = (rng.uniform(0.12, 0.88, size=3) * dims).astype(np.float32)
-        r = np.float32(rng.uniform(0.03 * m, 0.10 * m))
+        r = np.float32(rng.uniform(0.03 * m, 0.10 * m) * rscale)
         r2 = np.float32(rng.uniform(0.3, 0.5)) * r
         ext = int(np.ceil(r + r2 + 2))
         lo = np.maximum(np.floor(c).astype(int) - ext, 0)
@@ -125,8 +131,8 @@ WORKLOADS = {
     "sphere64": lambda z0=None, z1=None: sphere(64, z0, z1),
     "torus256": lambda z0=None, z1=None: torus(256, z0=z0, z1=z1),
     "twist512": lambda z0=None, z1=None: twist(512, z0, z1),
-    "assembly1024": lambda z0=None, z1=None: assembly(1024, z0=z0, z1=z1),
-    "stress2048": lambda z0=None, z1=None: assembly(2048, count=160, z0=z0, z1=z1),
+    "assembly1024": lambda z0=None, z1=None: assembly(1024, z0=z0, z1=z1, rscale=ASSEMBLY_RSCALE),
+    "stress2048": lambda z0=None, z1=None: assembly(2048, count=160, z0=z0, z1=z1, rscale=ASSEMBLY_RSCALE),
 }
 
 
@@ -147,7 +153,7 @@ def make(name: str, n=None, z0=None, z1=None) -> np.ndarray:
         cnt = 64 if fam == "assembly" else 160
         if not np.isscalar(n):  # keep the solid density of the cubic workload
             cnt = max(1, int(round(cnt * (n[0] * n[1] * n[2]) / float(max(n)) ** 3)))
-        return assembly(n, count=cnt, z0=z0, z1=z1)
+        return assembly(n, count=cnt, z0=z0, z1=z1, rscale=ASSEMBLY_RSCALE if m >= 256 else 1.0)
     raise KeyError(name)
 
 
