@@ -380,14 +380,17 @@ def run_ours(args):
             ctx.lib.vc_download(ctx.h, which, outs[k].array.ctypes.data)
 
     def time_e2e(fn):
-        e2e_steps = max(2, min(args.steps, 5))
+        """seconds per call: median of individually timed calls (each call ends with its own stream syncs), max over ranks"""
+        reps = max(3, min(args.steps, 10))
         fn()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
             fn()
+            ts.append(time.perf_counter() - t0)
         barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
+        dt = float(np.median(ts))
         if dist is not None:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

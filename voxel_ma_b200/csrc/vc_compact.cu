@@ -12,6 +12,7 @@
 // Order: ascending linear vertex index, fixed by an exclusive prefix over the popcounts of the
 // occupancy bit rows -- no atomics, so the record order is deterministic and a z chunk of the
 // pipeline owns one contiguous range of records that can start its copy as soon as the chunk is done.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -230,6 +231,15 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// P[z] = rowpre[z * ny]: the record index at which plane z starts (z = 0 .. nplanes), gathered on the device so that
+// ONE small copy brings it to the host (a strided 2-D copy of 4-byte rows costs hundreds of microseconds)
+__global__ void k_plane_starts(const u32* __restrict__ rowpre, int ny, int nplanes, u32* __restrict__ P)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z <= nplanes)
+        P[z] = rowpre[(size_t)z * ny];
+}
+
 // row prefix of the owned planes, queued on c->stream; the plane-boundary values P[0..nplanes] are
 // copied to host_P (pinned) by the same stream -- valid after the caller's next synchronisation
 static int compact_prefix_async(vc_ctx* c, u32* host_P)
@@ -239,13 +249,17 @@ static int compact_prefix_async(vc_ctx* c, u32* host_P)
     const size_t nrows = (size_t)c->ny * (size_t)(c->z1 - c->z0);
     if ((size_t)c->nx * nrows >= (1ull << 32))
         return vc_fail(c, VC_ERR_UNSUPPORTED, "compact records index vertices with 32 bits: slab too large");
-    VC_CUDA(c, c->rowpre.ensure((nrows + 2) * 4));
+    const int nplanes = c->z1 - c->z0;
+    VC_CUDA(c, c->rowpre.ensure((nrows + 2 + (size_t)nplanes + 2) * 4));
     const u32* bits = c->bits.as<u32>() + (size_t)(c->z0 - c->zlo) * c->ny * (size_t)c->wr;
     VC_LAUNCH(c, "row_popc", k_row_popc, vc_blocks((nrows + 1) * 32, 256), 256, 0, bits, c->wr, nrows, c->rowpre.as<u32>());
     VC_TRY(vc_exclusive_scan_u32(c, c->rowpre.as<u32>(), (int64_t)nrows + 1));
     if (host_P)
-        VC_CUDA(c, cudaMemcpy2DAsync(host_P, 4, c->rowpre.p, (size_t)c->ny * 4, 4, (size_t)(c->z1 - c->z0) + 1,
-                                     cudaMemcpyDeviceToHost, c->stream));
+    {
+        u32* P = c->rowpre.as<u32>() + nrows + 2;
+        VC_LAUNCH(c, "plane_starts", k_plane_starts, vc_blocks((size_t)nplanes + 1, 256), 256, 0, c->rowpre.as<u32>(), c->ny, nplanes, P);
+        VC_CUDA(c, cudaMemcpyAsync(host_P, P, ((size_t)nplanes + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     return VC_OK;
 }
 
@@ -373,7 +387,10 @@ extern "C"
         c->have_vol = true;
         c->have_inside = c->have_sites = c->have_closest = c->have_measures = false;
         const bool trace = getenv("VC_TRACE") != nullptr; // development aid: where the call's time goes
-        cudaEvent_t tev[6] = {};
+        cudaEvent_t tev[8] = {};
+        double host_t[8] = {};
+        const auto host_t0 = std::chrono::steady_clock::now();
+        auto host_mark = [&](int i) { host_t[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
         auto mark = [&](int i, cudaStream_t st)
         {
             if (trace)
@@ -399,7 +416,21 @@ extern "C"
             VC_CUDA(c, cudaStreamWaitEvent(c->stream, ev, 0));
             VC_CUDA(c, cudaEventDestroy(ev));
             if (chunked)
+            {
                 VC_TRY(st_classify_planes(c, z, ze));
+                // the chunk's occupancy bit rows go back while later chunks are still coming in (the device-to-host
+                // direction is idle during the upload); left for later they would sit in front of the small
+                // count read-back in the copy queue
+                if (inside_bits)
+                {
+                    const size_t r0 = (size_t)z * c->ny * (size_t)c->wr, rn = (size_t)(ze - z) * c->ny * (size_t)c->wr;
+                    VC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    VC_CUDA(c, cudaEventRecord(ev, c->stream));
+                    VC_CUDA(c, cudaStreamWaitEvent(c->s_d2h, ev, 0));
+                    VC_CUDA(c, cudaEventDestroy(ev));
+                    VC_CUDA(c, cudaMemcpyAsync(inside_bits + r0, c->bits.as<u32>() + r0, rn * 4, cudaMemcpyDefault, c->s_d2h));
+                }
+            }
         }
         if (!chunked)
             VC_TRY(st_classify_planes(c, 0, c->nz));
@@ -414,14 +445,18 @@ extern "C"
             VC_CUDA(c, cudaEventDestroy(ev));
             return VC_OK;
         };
-        if (inside_bits)
+        const bool bits_later = inside_bits && !chunked;
+        u32* P = (u32*)c->pinned + 16;
+        VC_TRY(compact_prefix_async(c, P));
+        host_mark(0);
+        VC_TRY(st_detect_sites(c)); // synchronises the main stream: site count, and P is valid
+        host_mark(1);
+        mark(6, c->stream);
+        if (bits_later)
         {
             VC_TRY(after_main(c->s_d2h));
             VC_CUDA(c, cudaMemcpyAsync(inside_bits, c->bits.p, (size_t)c->ny * c->nz * (size_t)c->wr * 4, cudaMemcpyDefault, c->s_d2h));
         }
-        u32* P = (u32*)c->pinned + 16;
-        VC_TRY(compact_prefix_async(c, P));
-        VC_TRY(st_detect_sites(c)); // synchronises the main stream: site count, and P is valid
         const int64_t n = (int64_t)P[c->nz];
         c->ninside = n;
         if (n_inside)
@@ -433,6 +468,7 @@ extern "C"
         }
         VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
         mark(3, c->stream);
+        host_mark(2);
         VC_TRY(compact_alloc(c, n, true));
         std::vector<u32> Ph(P, P + c->nz + 1); // the pinned scratch is reused by later stages
         // few inside vertices: their measures go straight into the records and the 8 dense float planes are
@@ -461,15 +497,19 @@ extern "C"
         c->skip_dense_measures = false;
         mark(4, c->stream);
         mark(5, c->s_d2h);
+        host_mark(3);
         cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
         if (trace && e1 == cudaSuccess && e2 == cudaSuccess)
         {
-            float t[6] = {0};
-            for (int i = 1; i < 6; ++i)
+            float t[8] = {0};
+            for (int i = 1; i < 7; ++i)
                 cudaEventElapsedTime(&t[i], tev[0], tev[i]);
-            fprintf(stderr, "[vc trace] upload done %.3f | classified %.3f | sites numbered %.3f | transform+records %.3f | "
-                            "copied back %.3f ms\n", t[1], t[2], t[3], t[4], t[5]);
-            for (int i = 0; i < 6; ++i)
+            host_mark(4);
+            fprintf(stderr, "[vc trace] upload done %.3f | classified %.3f | sites detected %.3f | sites numbered %.3f | "
+                            "transform+records %.3f | copied back %.3f ms   (host: upload queued %.3f, count known %.3f, numbering queued "
+                            "%.3f, pipeline queued %.3f, all done %.3f)\n", t[1], t[2], t[6], t[3], t[4], t[5], host_t[0], host_t[1],
+                    host_t[2], host_t[3], host_t[4]);
+            for (int i = 0; i < 7; ++i)
                 cudaEventDestroy(tev[i]);
         }
         VC_TRY(hook_status);

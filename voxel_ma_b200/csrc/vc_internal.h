@@ -90,6 +90,8 @@ struct vc_ctx
     DevBuf site_key, site_corner, site_xyz; // u64, u64, float4 in id order
     int64_t nsites = 0;
     DevBuf line_ptr, line_ent; // z-line lists: int32[(nx+1)(ny+1)+1], u64 (cz<<32|id)
+    DevBuf scan_sums;          // block totals of vc_exclusive_scan_u32
+    DevBuf line_cur;           // per-column fill cursors while the lists are built
     DevBuf colmask;            // u32[ny+1][(nx+32)/32] bit rows: column (cx,cy) has sites (pass Z writes, pass X reads only those)
     // transform scratch + results
     DevBuf g1, g2, id, d2, edge3, face3, cube, radius;

@@ -677,14 +677,6 @@ __global__ void __launch_bounds__(256, 4)
 
 // note: the histogram kernel tiles by (item, thread) and the scatter by (warp, item, lane); both
 // cover exactly [tile*RS_TILE, (tile+1)*RS_TILE), which is all the per-tile counts depend on.
-// exclusive prefix of len u32 values in place (device), on stream c->cur
-int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len)
-{
-    VC_LAUNCH(c, "scan_u32", k_rs_scan, 1, 1024, 0, a, len);
-    VC_CUDA(c, cudaGetLastError());
-    return VC_OK;
-}
-
 int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io)
 {
     if (n <= 1)
@@ -836,6 +828,221 @@ __global__ void k_count_dups(const u64* __restrict__ k, int64_t n, u64* counter)
         atomicAdd(counter, 1ull);
 }
 
+// ---- z-line lists by counting (no second sort) -----------------------------------------------------
+// The lists only need the sites of each column (cx,cy) in ascending cz.  Counting does that in O(S):
+// per-column counts (atomics) -> exclusive scan = line_ptr -> every site takes a slot of its column
+// (atomics, arbitrary order) -> each column orders its own few entries by (cz, id).  The final lists
+// do not depend on the order in which the atomics were served.
+__global__ void k_line_count(const u64* __restrict__ site_corner, int64_t n, int CY, u32* __restrict__ cnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int cx, cy, cz;
+    vc_unpack_corner(site_corner[i], cx, cy, cz);
+    atomicAdd(&cnt[(size_t)cx * CY + cy], 1u);
+}
+
+// exclusive scan of len u32 values, several blocks: (1) each block scans its 4096 values in place and reports its
+// total, (2) the totals are scanned by one block (k_rs_scan), (3) every value gets its block's offset
+__global__ void __launch_bounds__(1024) k_scan_blocks(u32* __restrict__ a, int64_t len, u32* __restrict__ sums)
+{
+    __shared__ u32 wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = ((int64_t)blockIdx.x * 1024 + threadIdx.x) * 4;
+    u32 v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        v[k] = (i0 + k < len) ? a[i0 + k] : 0u;
+        s += v[k];
+    }
+    u32 inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    if (lane == 31)
+        wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        u32 w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += t;
+        }
+        wsum[lane] = wi - w;
+        if (lane == 31)
+            sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    u32 excl = wsum[warp] + inc - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        if (i0 + k < len)
+            a[i0 + k] = excl;
+        excl += v[k];
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(u32* __restrict__ a, int64_t len, const u32* __restrict__ sums)
+{
+    const u32 off = sums[blockIdx.x];
+    const int64_t i0 = ((int64_t)blockIdx.x * 1024 + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i0 + k < len)
+            a[i0 + k] += off;
+}
+
+__global__ void k_line_fill(const u64* __restrict__ site_corner, int64_t n, int CY, u32* __restrict__ cursor, u64* __restrict__ tmp)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int cx, cy, cz;
+    vc_unpack_corner(site_corner[i], cx, cy, cz);
+    const u32 pos = atomicAdd(&cursor[(size_t)cx * CY + cy], 1u);
+    tmp[pos] = ((u64)(u32)cz << 32) | (u32)i;
+}
+
+// columns with up to LS_SHORT entries: one thread orders them with a compare-exchange network on the (cz, id)
+// words; longer ones are queued for k_line_sort_long.  dups (nullable) counts equal cz inside a column (external
+// sets with repeated points).
+#define LS_SHORT 4
+__device__ __forceinline__ void ls_cx(u64& a, u64& b)
+{
+    const u64 lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo;
+    b = hi;
+}
+__global__ void k_line_sort_short(const int* __restrict__ line_ptr, int nlines, const u64* __restrict__ tmp, u64* __restrict__ ent,
+                                  u32* __restrict__ long_lines, u32* __restrict__ nlong, u64* __restrict__ dups)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines)
+        return;
+    const int b = line_ptr[l], cnt = line_ptr[l + 1] - b;
+    if (cnt == 0)
+        return;
+    if (cnt == 1)
+    {
+        ent[b] = tmp[b];
+        return;
+    }
+    if (cnt > LS_SHORT)
+    {
+        long_lines[atomicAdd(nlong, 1u)] = (u32)l;
+        return;
+    }
+    u64 e0 = tmp[b], e1 = tmp[b + 1], e2 = cnt > 2 ? tmp[b + 2] : VC_INF, e3 = cnt > 3 ? tmp[b + 3] : VC_INF;
+    ls_cx(e0, e1); // optimal 4-input network: (0,1)(2,3)(0,2)(1,3)(1,2)
+    ls_cx(e2, e3);
+    ls_cx(e0, e2);
+    ls_cx(e1, e3);
+    ls_cx(e1, e2);
+    ent[b] = e0;
+    ent[b + 1] = e1;
+    if (cnt > 2)
+        ent[b + 2] = e2;
+    if (cnt > 3)
+        ent[b + 3] = e3;
+    if (dups)
+    {
+        const u32 nd = ((e0 >> 32) == (e1 >> 32)) + (cnt > 2 && (e1 >> 32) == (e2 >> 32)) + (cnt > 3 && (e2 >> 32) == (e3 >> 32));
+        if (nd)
+            atomicAdd(dups, (u64)nd);
+    }
+}
+
+// Longer columns: one warp per column.  The cz of a column's sites are distinct corner indices in [0, nz], so the
+// column is ordered by presence: a bitmap of nz+1 bits in shared memory, rank = number of set bits below cz.
+// A bit found already set is a repeated point (only possible for external sets): it is counted in dups, which
+// makes the caller fall back to the general search -- the lists are then not used.
+#define LS_WORDS 65 // 2049 bits + padding: sides up to 2048
+__global__ void __launch_bounds__(256)
+    k_line_sort_long(const int* __restrict__ line_ptr, const u64* __restrict__ tmp, u64* __restrict__ ent,
+                     const u32* __restrict__ long_lines, const u32* __restrict__ nlong, u64* __restrict__ dups)
+{
+    __shared__ u32 bitsm[8][LS_WORDS + 1], pre[8][LS_WORDS + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 nl = *nlong;
+    for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nl; j += (gridDim.x * blockDim.x) >> 5)
+    {
+        const int l = (int)long_lines[j];
+        const int b = line_ptr[l], cnt = line_ptr[l + 1] - b;
+        for (int w = lane; w <= LS_WORDS; w += 32)
+            bitsm[warp][w] = 0;
+        __syncwarp();
+        u32 nd = 0;
+        for (int i = lane; i < cnt; i += 32)
+        {
+            const u32 cz = (u32)(tmp[b + i] >> 32);
+            const u32 old = atomicOr(&bitsm[warp][cz >> 5], 1u << (cz & 31));
+            nd += (old >> (cz & 31)) & 1u;
+        }
+        __syncwarp();
+        // exclusive prefix of the word popcounts (LS_WORDS <= 96: three rounds of 32)
+        u32 carry = 0;
+        for (int w0 = 0; w0 <= LS_WORDS; w0 += 32)
+        {
+            const int w = w0 + lane;
+            const u32 v = w <= LS_WORDS ? __popc(bitsm[warp][w]) : 0u;
+            u32 inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t;
+            }
+            if (w <= LS_WORDS)
+                pre[warp][w] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32)
+        {
+            const u64 me = tmp[b + i];
+            const u32 cz = (u32)(me >> 32);
+            const u32 rank = pre[warp][cz >> 5] + __popc(bitsm[warp][cz >> 5] & ((1u << (cz & 31)) - 1u));
+            ent[b + (rank < (u32)cnt ? rank : (u32)cnt - 1)] = me;
+        }
+        if (nd && dups)
+            atomicAdd(dups, (u64)nd);
+        __syncwarp();
+    }
+}
+
+// exclusive prefix of len u32 values in place (device), on stream c->cur: one block for short arrays, otherwise
+// block-local scans + a scan of the block totals + an add pass (a single block over 10^5..10^6 values is ~0.1 ms)
+int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len)
+{
+    if (len <= 8192)
+    {
+        VC_LAUNCH(c, "scan_u32", k_rs_scan, 1, 1024, 0, a, len);
+    }
+    else
+    {
+        const unsigned sblocks = vc_blocks((size_t)len, 4096);
+        VC_CUDA(c, c->scan_sums.ensure(((size_t)sblocks + 2) * 4));
+        u32* sums = c->scan_sums.as<u32>();
+        VC_LAUNCH(c, "scan_u32", k_scan_blocks, sblocks, 1024, 0, a, len, sums);
+        VC_LAUNCH(c, "scan_u32", k_rs_scan, 1, 1024, 0, sums, (int64_t)sblocks);
+        VC_LAUNCH(c, "scan_u32", k_scan_add, sblocks, 1024, 0, a, len, sums);
+    }
+    VC_CUDA(c, cudaGetLastError());
+    return VC_OK;
+}
+
 static int bits_for(u64 maxval)
 {
     int b = 1;
@@ -888,11 +1095,42 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
     u32* v2 = (v == c->sv0.as<u32>()) ? c->sv1.as<u32>() : c->sv0.as<u32>();
     VC_LAUNCH(c, "site_tables", k_site_tables, blocks, 256, 0, order, corners_dev, ksorted, c->site_key.as<u64>(),
               c->site_corner.as<u64>(), c->site_xyz.as<float4>(), k2, v2, n, c->ny, c->nz);
-    u64 maxkey2 = (u64)nlines * (u64)(c->nz + 1);
-    VC_TRY(vc_radix_sort_pairs(c, n, bits_for(maxkey2), &k2, &v2));
-    VC_LAUNCH(c, "line_entries", k_line_entries, blocks, 256, 0, k2, v2, c->line_ent.as<u64>(), n, c->nz);
-    VC_LAUNCH(c, "line_ptr", k_line_ptr, vc_blocks((size_t)nlines + 1, 256), 256, 0, k2, n, nlines, c->nz,
-              c->line_ptr.as<int>());
+    u64* counter = c->scratch.as<u64>();
+    static const bool lines_by_sort = getenv("VC_LINES") && !strcmp(getenv("VC_LINES"), "sort");
+    if (lines_by_sort)
+    { // the earlier formulation, kept for A/B runs: a second radix sort on (line, cz)
+        u64 maxkey2 = (u64)nlines * (u64)(c->nz + 1);
+        VC_TRY(vc_radix_sort_pairs(c, n, bits_for(maxkey2), &k2, &v2));
+        VC_LAUNCH(c, "line_entries", k_line_entries, blocks, 256, 0, k2, v2, c->line_ent.as<u64>(), n, c->nz);
+        VC_LAUNCH(c, "line_ptr", k_line_ptr, vc_blocks((size_t)nlines + 1, 256), 256, 0, k2, n, nlines, c->nz,
+                  c->line_ptr.as<int>());
+        if (!sort_by_key)
+        {
+            VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+            VC_LAUNCH(c, "count_dups", k_count_dups, blocks, 256, 0, k2, n, counter);
+        }
+    }
+    else
+    {
+        const int CY = c->ny + 1;
+        const int64_t len = (int64_t)nlines + 1;
+        u32* ptr = c->line_ptr.as<u32>();
+        VC_CUDA(c, c->line_cur.ensure((size_t)(nlines + 2) * 4));
+        u32* cursor = c->line_cur.as<u32>();
+        VC_CUDA(c, c->shist.ensure(((size_t)nlines + 4) * 4));
+        u32* long_lines = c->shist.as<u32>(); // [0] = count, then the queued columns
+        VC_CUDA(c, cudaMemsetAsync(ptr, 0, (size_t)(nlines + 2) * 4, c->stream));
+        VC_CUDA(c, cudaMemsetAsync(long_lines, 0, 4, c->stream));
+        VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+        VC_LAUNCH(c, "line_count", k_line_count, blocks, 256, 0, c->site_corner.as<u64>(), n, CY, ptr);
+        VC_TRY(vc_exclusive_scan_u32(c, ptr, len));
+        VC_CUDA(c, cudaMemcpyAsync(cursor, ptr, (size_t)(nlines + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        VC_LAUNCH(c, "line_fill", k_line_fill, blocks, 256, 0, c->site_corner.as<u64>(), n, CY, cursor, k2);
+        VC_LAUNCH(c, "line_sort", k_line_sort_short, vc_blocks((size_t)nlines, 256), 256, 0, c->line_ptr.as<int>(), nlines, k2,
+                  c->line_ent.as<u64>(), long_lines + 1, long_lines, sort_by_key ? (u64*)nullptr : counter);
+        VC_LAUNCH(c, "line_sort", k_line_sort_long, c->sm_count * 2, 256, 0, c->line_ptr.as<int>(), k2, c->line_ent.as<u64>(),
+                  long_lines + 1, long_lines, sort_by_key ? (u64*)nullptr : counter);
+    }
     {
         const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
         VC_LAUNCH(c, "line_mask", k_line_mask, vc_blocks((size_t)CY * nw, 256), 256, 0, c->line_ptr.as<int>(), CX, CY, nw,
@@ -900,9 +1138,6 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
     }
     if (!sort_by_key)
     { // external set: duplicates on the lattice would need the lowest-id rule inside a list entry
-        u64* counter = c->scratch.as<u64>();
-        VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
-        VC_LAUNCH(c, "count_dups", k_count_dups, blocks, 256, 0, k2, n, counter);
         u64 d = 0;
         VC_CUDA(c, cudaMemcpyAsync(&d, counter, 8, cudaMemcpyDeviceToHost, c->stream));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
