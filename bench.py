@@ -413,24 +413,27 @@ def run_ours(args):
     # (vertex, id, 4d2, 7 lambda, radius) per INSIDE vertex out.  Measures anchored at outside vertices are 0
     # by definition, so nothing is lost; the dense planes are still computed in HBM.
     e2e_s, d2h = e2e_planes_s, d2h_planes
-    if world == 1:
+    if world == 1 or state.get("peers") is not None:
         del outs
         n_in = ctx.compact_count()
         cap = n_in + 1024
         wr = nx // 32 + 1
-        cb = {"bits": api.PinnedArray((nz * ny, wr), np.uint32), "vert": api.PinnedArray((cap,), np.uint32),
+        cb = {"bits": api.PinnedArray(((z1 - z0) * ny, wr), np.uint32), "vert": api.PinnedArray((cap,), np.uint32),
               "id": api.PinnedArray((cap,), np.int32), "d2": api.PinnedArray((cap,), np.uint32),
               "lam": api.PinnedArray((7, cap), np.float32), "rad": api.PinnedArray((cap,), np.float32)}
 
         def step_compact(dense=None):
+            # on a slab ctx the same call uploads the rank's planes and exchanges the site records over peer memory
             return ctx.run_dense_host_compact(pin_vol.array, cap, cb["bits"].array, cb["vert"].array, cb["id"].array, cb["d2"].array,
                                               cb["lam"].array, cb["rad"].array, *(dense or (None, None)))
 
         e2e_s = time_e2e(step_compact)
-        d2h = int(cb["bits"].array.nbytes + n_in * 44)
+        (d2h,) = total(int(cb["bits"].array.nbytes + n_in * 44))
+        (n_in_total,) = total(n_in)
         # the e2e result really is the device result: spot-check the records against the resident planes
         got_n, _ = step_compact()
-        ctx.run_dense()  # the dense planes (the compact step computes the records of few inside vertices directly)
+        step()  # the dense planes (the compact step computes the records of few inside vertices directly)
+        ctx.synchronize()
         ids_dev = ctx.download(api.ARR_ID).ravel()
         cube_dev = ctx.download(api.ARR_CUBE).ravel()
         v = cb["vert"].array[:got_n]
@@ -438,9 +441,9 @@ def run_ours(args):
             raise SystemExit("compact e2e records disagree with the dense planes")
         del ids_dev, cube_dev
         e2e_variants["compact"] = {"value": nv_total / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                   "inside_vertices": n_in,
+                                   "inside_vertices": n_in_total,
                                    "result": "occupancy bit rows + (vertex u32, id i32, 4d2 u32, 7 lambda f32, radius f32) per inside vertex"}
-        dense = (api.PinnedArray((nz, ny, nx), np.int32), api.PinnedArray((nz, ny, nx), np.uint32))
+        dense = (api.PinnedArray((z1 - z0, ny, nx), np.int32), api.PinnedArray((z1 - z0, ny, nx), np.uint32))
         dt = time_e2e(lambda: step_compact((dense[0].array, dense[1].array)))
         e2e_variants["compact_plus_dense_ids"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
                                                   "d2h_bytes_per_step": d2h + 8 * nv_total,

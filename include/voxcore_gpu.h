@@ -246,7 +246,10 @@ int vc_run_dense_host(vc_ctx* ctx, const float* vol, uint8_t* inside, int32_t* i
  *                       z chunk copied back while the next chunk computes.  inside_bits (nullable):
  *                       uint32 [nz*ny][nx/32+1], bit x&31 of word x>>5.  id_dense / d2x4_dense
  *                       (nullable): the full planes as well.  cap < count -> VC_ERR_NOMEM with the
- *                       count in *n_inside.
+ *                       count in *n_inside.  On a slab ctx (one rank of a peer group, vc_peer_open):
+ *                       vol = the slab's resident planes [max(z0-1,0), min(z1+1,nz)), outputs cover the
+ *                       owned planes, the site records travel through the peer exchange, and every rank
+ *                       of the group must make the call.
  *   vc_set_compact_mode how vc_run_dense_host_compact obtains the records: 1 = dense measure planes,
  *                       then gathered; 2 = computed directly per inside vertex (the 8 dense float
  *                       planes are then NOT produced by that call: vc_download of them fails with

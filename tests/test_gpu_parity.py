@@ -310,6 +310,63 @@ def test_peer_exchange_matches_the_gathered_import(ctx_factory):
         p.peer_close()
 
 
+def test_slab_group_host_compact_pipeline(ctx_factory):
+    """vc_run_dense_host_compact on the slab contexts of a peer group (the N>1 end-to-end step): every rank uploads
+    its own planes, the site records travel through the peer exchange, each rank gets the records of its owned
+    planes.  The ranks of one process run in threads (the call blocks until every rank has posted)."""
+    import threading
+    vol = synth.make("twist", 48)
+    nz, ny, nx = vol.shape
+    o_inside = ob.classify_grid(vol)
+    o_sites = ob.extract_sites(o_inside)
+    o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
+    oe, of, oc, orad = ob.cell_measures_grid(o_sites, o_ids, o_inside, nx, ny, nz)
+    cuts = [0, 17, 30, 48]
+    world = len(cuts) - 1
+    parts = [ctx_factory() for _ in range(world)]
+    for k, p in enumerate(parts):
+        p.set_grid(nx, ny, nz, cuts[k], cuts[k + 1])
+        p.peer_create(world, k, 40000)
+    bases = [p.peer_buffer() for p in parts]
+    for p in parts:
+        p.peer_open_ptrs(bases)
+    res, errs = [None] * world, []
+
+    def rank(k):
+        try:
+            z0, z1 = cuts[k], cuts[k + 1]
+            lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
+            cap = int(o_inside[z0:z1].sum()) + 5
+            out = dict(bits=np.empty(((z1 - z0) * ny, nx // 32 + 1), np.uint32), vert=np.empty(cap, np.uint32), ids=np.empty(cap, np.int32),
+                       d2=np.empty(cap, np.uint32), lam=np.empty((7, cap), np.float32), rad=np.empty(cap, np.float32))
+            n_in, ns = parts[k].run_dense_host_compact(np.ascontiguousarray(vol[lo:hi]), cap, out["bits"], out["vert"], out["ids"], out["d2"],
+                                                       out["lam"], out["rad"])
+            res[k] = (n_in, ns, out)
+        except Exception as ex:  # surfaced below
+            errs.append(ex)
+
+    for _ in range(2):  # both parities of the exchange buffers
+        th = [threading.Thread(target=rank, args=(k,)) for k in range(world)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for k in range(world):
+            z0, z1 = cuts[k], cuts[k + 1]
+            n_in, ns, out = res[k]
+            where = np.flatnonzero(o_inside[z0:z1].ravel()).astype(np.uint32)
+            assert ns == len(o_sites) and n_in == len(where)
+            assert np.array_equal(out["vert"][:n_in], where)
+            assert np.array_equal(out["ids"][:n_in], o_ids[z0:z1].ravel()[where]) and np.array_equal(out["d2"][:n_in], o_d2[z0:z1].ravel()[where])
+            planes = [oe[0], oe[1], oe[2], of[0], of[1], of[2], oc]
+            for j, pl in enumerate(planes):
+                assert np.array_equal(out["lam"][j, :n_in], pl[z0:z1].ravel()[where]), (k, j)
+            assert np.array_equal(out["rad"][:n_in], orad[z0:z1].ravel()[where])
+            unpacked = np.unpackbits(out["bits"].reshape(z1 - z0, ny, -1).view(np.uint8), axis=-1, bitorder="little")[:, :, :nx]
+            assert np.array_equal(unpacked, o_inside[z0:z1])
+    for p in parts:
+        p.peer_close()
+
+
 def test_peer_exchange_errors_do_not_hang(ctx_factory):
     """a rank that never posts -> VC_ERR_STATE after the bounded wait; too small a capacity -> VC_ERR_NOMEM"""
     vol = synth.twist(24)

@@ -378,12 +378,18 @@ extern "C"
         if (!c || !vol || cap < 0)
             return VC_ERR_INVALID;
         VC_CUDA(c, cudaSetDevice(c->device));
-        if (!c->have_grid || c->z0 != 0 || c->z1 != c->nz)
-            return vc_fail(c, VC_ERR_STATE, "vc_run_dense_host_compact needs a ctx that owns the whole grid");
-        const size_t plane = (size_t)c->nx * c->ny, nv = plane * c->nz;
-        VC_CUDA(c, c->vol.ensure(nv * 4 + 64));
-        c->zlo = 0;
-        c->zhi = c->nz;
+        if (!c->have_grid)
+            return vc_fail(c, VC_ERR_STATE, "vc_run_dense_host_compact: call vc_set_grid first");
+        const bool slab = c->z0 != 0 || c->z1 != c->nz;
+        if (slab && c->peer_world < 2)
+            return vc_fail(c, VC_ERR_STATE, "vc_run_dense_host_compact on a slab needs the peer group of its ranks (vc_peer_create / "
+                                            "vc_peer_open)");
+        // resident voxel planes: the slab plus one halo plane on each interior side (what vc_volume_upload_f32 takes)
+        const int zlo = c->z0 > 0 ? c->z0 - 1 : 0, zhi = c->z1 < c->nz ? c->z1 + 1 : c->nz;
+        const size_t plane = (size_t)c->nx * c->ny, nv = plane * (size_t)(c->z1 - c->z0);
+        VC_CUDA(c, c->vol.ensure(plane * (size_t)(zhi - zlo) * 4 + 64));
+        c->zlo = zlo;
+        c->zhi = zhi;
         c->have_vol = true;
         c->have_inside = c->have_sites = c->have_closest = c->have_measures = false;
         const bool trace = getenv("VC_TRACE") != nullptr; // development aid: where the call's time goes
@@ -403,13 +409,13 @@ extern "C"
         VC_TRY(st_classify_begin(c));
         // upload in plane chunks on the copy stream; a chunk is classified as soon as it has landed
         const bool chunked = st_classify_chunkable(c);
-        const int nch = c->nz >= 32 ? 16 : 1;
-        const int chunk = (c->nz + nch - 1) / nch;
+        const int nch = zhi - zlo >= 32 ? 16 : 1;
+        const int chunk = (zhi - zlo + nch - 1) / nch;
         cudaEvent_t ev = nullptr;
-        for (int z = 0; z < c->nz; z += chunk)
+        for (int z = zlo; z < zhi; z += chunk)
         {
-            const int ze = z + chunk < c->nz ? z + chunk : c->nz;
-            const size_t off = plane * z, cnt = plane * (size_t)(ze - z);
+            const int ze = z + chunk < zhi ? z + chunk : zhi;
+            const size_t off = plane * (size_t)(z - zlo), cnt = plane * (size_t)(ze - z);
             VC_CUDA(c, cudaMemcpyAsync(c->vol.as<float>() + off, vol + off, cnt * 4, cudaMemcpyDefault, c->s_h2d));
             VC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             VC_CUDA(c, cudaEventRecord(ev, c->s_h2d));
@@ -421,19 +427,21 @@ extern "C"
                 // the chunk's occupancy bit rows go back while later chunks are still coming in (the device-to-host
                 // direction is idle during the upload); left for later they would sit in front of the small
                 // count read-back in the copy queue
-                if (inside_bits)
+                const int oa = z > c->z0 ? z : c->z0, ob = ze < c->z1 ? ze : c->z1; // owned planes of this chunk
+                if (inside_bits && oa < ob)
                 {
-                    const size_t r0 = (size_t)z * c->ny * (size_t)c->wr, rn = (size_t)(ze - z) * c->ny * (size_t)c->wr;
+                    const size_t rw = (size_t)c->ny * (size_t)c->wr;
                     VC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                     VC_CUDA(c, cudaEventRecord(ev, c->stream));
                     VC_CUDA(c, cudaStreamWaitEvent(c->s_d2h, ev, 0));
                     VC_CUDA(c, cudaEventDestroy(ev));
-                    VC_CUDA(c, cudaMemcpyAsync(inside_bits + r0, c->bits.as<u32>() + r0, rn * 4, cudaMemcpyDefault, c->s_d2h));
+                    VC_CUDA(c, cudaMemcpyAsync(inside_bits + (size_t)(oa - c->z0) * rw, c->bits.as<u32>() + (size_t)(oa - zlo) * rw,
+                                               (size_t)(ob - oa) * rw * 4, cudaMemcpyDefault, c->s_d2h));
                 }
             }
         }
         if (!chunked)
-            VC_TRY(st_classify_planes(c, 0, c->nz));
+            VC_TRY(st_classify_planes(c, zlo, zhi));
         c->have_inside = true;
         mark(1, c->s_h2d);
         mark(2, c->stream);
@@ -449,15 +457,24 @@ extern "C"
         u32* P = (u32*)c->pinned + 16;
         VC_TRY(compact_prefix_async(c, P));
         host_mark(0);
-        VC_TRY(st_detect_sites(c)); // synchronises the main stream: site count, and P is valid
+        // numbering the sites synchronises the main stream (site count), after which P is valid too
+        int64_t n_all = 0;
+        if (c->peer_world > 1)
+        { // slab group: the detection kernel stores the records into every rank, the union is numbered everywhere
+            VC_TRY(vc_sites_post_peers(c));
+            VC_TRY(vc_sites_collect_peers(c, &n_all));
+        }
+        else
+            VC_TRY(st_detect_sites(c));
         host_mark(1);
         mark(6, c->stream);
         if (bits_later)
         {
             VC_TRY(after_main(c->s_d2h));
-            VC_CUDA(c, cudaMemcpyAsync(inside_bits, c->bits.p, (size_t)c->ny * c->nz * (size_t)c->wr * 4, cudaMemcpyDefault, c->s_d2h));
+            VC_CUDA(c, cudaMemcpyAsync(inside_bits, c->bits.as<u32>() + (size_t)(c->z0 - zlo) * c->ny * (size_t)c->wr,
+                                       (size_t)c->ny * (size_t)(c->z1 - c->z0) * (size_t)c->wr * 4, cudaMemcpyDefault, c->s_d2h));
         }
-        const int64_t n = (int64_t)P[c->nz];
+        const int64_t n = (int64_t)P[c->z1 - c->z0];
         c->ninside = n;
         if (n_inside)
             *n_inside = n;
@@ -466,11 +483,12 @@ extern "C"
             cudaStreamSynchronize(c->s_d2h);
             return vc_fail(c, VC_ERR_NOMEM, "vc_run_dense_host_compact: capacity below the inside count (returned in n_inside)");
         }
-        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+        if (c->peer_world < 2)
+            VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
         mark(3, c->stream);
         host_mark(2);
         VC_TRY(compact_alloc(c, n, true));
-        std::vector<u32> Ph(P, P + c->nz + 1); // the pinned scratch is reused by later stages
+        std::vector<u32> Ph(P, P + (c->z1 - c->z0) + 1); // the pinned scratch is reused by later stages
         // few inside vertices: their measures go straight into the records and the 8 dense float planes are
         // never written; many: the tiled dense kernel reuses neighbours better, records are gathered from it
         const bool sparse = c->compact_mode == 2 || (c->compact_mode == 0 && (size_t)n * 8 <= nv);
@@ -484,8 +502,8 @@ extern "C"
             VC_CUDA(c, cudaEventRecord(e2, c->cur));
             VC_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e2, 0));
             VC_CUDA(c, cudaEventDestroy(e2));
-            VC_TRY(compact_copy_out(c, c->s_d2h, Ph[za], Ph[zb], cap, vert, id, d2x4, lambda7, radius));
-            const size_t o = plane * (size_t)za, m = plane * (size_t)(zb - za);
+            VC_TRY(compact_copy_out(c, c->s_d2h, Ph[za - c->z0], Ph[zb - c->z0], cap, vert, id, d2x4, lambda7, radius));
+            const size_t o = plane * (size_t)(za - c->z0), m = plane * (size_t)(zb - za);
             if (id_dense)
                 VC_CUDA(c, cudaMemcpyAsync(id_dense + o, c->id.as<int>() + o, m * 4, cudaMemcpyDefault, c->s_d2h));
             if (d2x4_dense)

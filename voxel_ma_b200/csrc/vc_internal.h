@@ -182,6 +182,8 @@ int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len);
 int st_detect_sites(vc_ctx* c);
 int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter);
 void vc_peer_release(vc_ctx* c);
+extern "C" int vc_sites_post_peers(vc_ctx* c);
+extern "C" int vc_sites_collect_peers(vc_ctx* c, int64_t* n_all);
 int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key);
 int st_closest_lattice(vc_ctx* c);
 int st_measures(vc_ctx* c, bool want_radius);

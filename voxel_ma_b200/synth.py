@@ -89,13 +89,13 @@ def twist(n: int = 512, z0=None, z1=None) -> np.ndarray:
 ASSEMBLY_RSCALE = 0.67
 
 
-def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None, rscale: float = 1.0) -> np.ndarray:
+def assembly(n=1024, count: int = 64, seed: int = 20181, z0=None, z1=None, rscale: float = 1.0, size_ref=None) -> np.ndarray:
     """Union of `count` solids (spheres, tori, boxes) with centres / radii drawn from
     mt19937(seed).  ``n`` is a side length or an (nx, ny, nz) triple; solids are placed in the unit
     cube and scaled per axis extent, sized by the smallest side; `rscale` scales every radius.  Built
     solid by solid on each solid's bounding box only, so a rank can generate just its own z-slab."""
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
-    m = min(nx, ny, nz)
+    m = min(nx, ny, nz) if size_ref is None else size_ref  # the side the radii are relative to
     rng = np.random.Generator(np.random.MT19937(seed))  # mt19937; seeded deterministically
     nz0 = 0 if z0 is None else z0
     nz1 = nz if z1 is None else z1
@@ -153,7 +153,10 @@ def make(name: str, n=None, z0=None, z1=None) -> np.ndarray:
         cnt = 64 if fam == "assembly" else 160
         if not np.isscalar(n):  # keep the solid density of the cubic workload
             cnt = max(1, int(round(cnt * (n[0] * n[1] * n[2]) / float(max(n)) ** 3)))
-        return assembly(n, count=cnt, z0=z0, z1=z1, rscale=ASSEMBLY_RSCALE if m >= 256 else 1.0)
+        # parts of the cube (the weak-scaling grids 512x512x1024, 512x1024x1024): solids as large as in the full cube, their
+        # number scaled with the volume, so the boundary samples per grid vertex stay what they are at assembly1024
+        ref = None if np.isscalar(n) else max(n)
+        return assembly(n, count=cnt, z0=z0, z1=z1, rscale=ASSEMBLY_RSCALE if m >= 256 else 1.0, size_ref=ref)
     raise KeyError(name)
 
 
