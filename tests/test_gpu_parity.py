@@ -330,16 +330,32 @@ def test_slab_group_host_compact_pipeline(ctx_factory):
     bases = [p.peer_buffer() for p in parts]
     for p in parts:
         p.peer_open_ptrs(bases)
+    # One lock-step round first, from this thread, so that every device buffer exists: in ONE process a cudaMalloc /
+    # cudaFree of one rank waits for the whole device, i.e. for another rank's wait kernel, which waits for this
+    # rank's post (one process per GPU has no such coupling; here it would only trip the bounded wait).
+    pins = []
+    for k, p in enumerate(parts):
+        z0, z1 = cuts[k], cuts[k + 1]
+        lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
+        pv = api.PinnedArray((hi - lo, ny, nx), np.float32)
+        pv.array[...] = vol[lo:hi]
+        pins.append(pv)
+        p.upload_volume(pv.array, zlo=lo)
+        p.classify_grid(fetch=False)
+        p.sites_post_peers()
+    for p in parts:
+        p.sites_collect_peers()
+        p.closest_and_measures()
+        p.compact_records()
     res, errs = [None] * world, []
 
     def rank(k):
         try:
             z0, z1 = cuts[k], cuts[k + 1]
-            lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
             cap = int(o_inside[z0:z1].sum()) + 5
             out = dict(bits=np.empty(((z1 - z0) * ny, nx // 32 + 1), np.uint32), vert=np.empty(cap, np.uint32), ids=np.empty(cap, np.int32),
                        d2=np.empty(cap, np.uint32), lam=np.empty((7, cap), np.float32), rad=np.empty(cap, np.float32))
-            n_in, ns = parts[k].run_dense_host_compact(np.ascontiguousarray(vol[lo:hi]), cap, out["bits"], out["vert"], out["ids"], out["d2"],
+            n_in, ns = parts[k].run_dense_host_compact(pins[k].array, cap, out["bits"], out["vert"], out["ids"], out["d2"],
                                                        out["lam"], out["rad"])
             res[k] = (n_in, ns, out)
         except Exception as ex:  # surfaced below

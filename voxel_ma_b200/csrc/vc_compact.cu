@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256)
 // Same arithmetic and the same validity rules as k_cell_measures (vc_measures.cu), evaluated per inside
 // anchor vertex from the id / d2x4 planes and the site table, without materialising the 8 dense float
 // planes (36 B per grid vertex of stores that are 0 wherever the anchor is outside).  One warp per bit
-// row; a lane owns one 32-vertex word of the row and walks its set bits.
+// row; the row's non-zero words are taken one after the other and the 32 vertices of a word are the 32 lanes.
 __device__ __forceinline__ float vc_dist2f_c(float4 a, float4 b)
 {
     float t = __fsub_rn(b.x, a.x);
@@ -134,100 +134,88 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 4; ++j)
         brow[j] = bits + ((size_t)(z + (j >> 1) - zlo) * ny + (size_t)(y + (j & 1))) * (size_t)wr;
     const bool rok[4] = {true, yok, zok, yok && zok};
-    for (int w0 = 0; w0 < wr; w0 += 32)
+    // word by word (warp-uniform), lane = bit: the 32 vertices of a word are evaluated in parallel
+    for (int w = 0; w < wr; ++w)
     {
-        const int w = w0 + lane;
-        u32 W[4] = {0, 0, 0, 0}, N[4] = {0, 0, 0, 0};
-        if (w < wr)
-        {
+        const u32 word = __ldg(brow[0] + w); // same address in every lane: one broadcast load
+        if (word == 0u)
+            continue;
+        u32 W[4] = {word, 0, 0, 0}, N[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (rok[j])
-                {
+        for (int j = 0; j < 4; ++j)
+            if (rok[j])
+            {
+                if (j)
                     W[j] = __ldg(brow[j] + w);
-                    N[j] = (w + 1 < wr) ? __ldg(brow[j] + w + 1) : 0u;
-                }
-        }
-        u32 word = W[0];
-        const int cnt = __popc(word);
-        int incl = cnt;
+                N[j] = (w + 1 < wr) ? __ldg(brow[j] + w + 1) : 0u;
+            }
+        const int b = lane;
+        const size_t pos = (size_t)base + (size_t)__popc(word & ((1u << b) - 1u));
+        base += (u32)__popc(word);
+        if (!((word >> b) & 1u))
+            continue;
+        const int x = 32 * w + b;
+        // inside flag and record (site position, has-site flag) of the cube vertex k = dx + 2*dy + 4*dz
+        bool in[8], has[8];
+        float4 r[8];
+        int own_id = -1;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
+        for (int k = 0; k < 8; ++k)
         {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        size_t pos = (size_t)base + (size_t)(incl - cnt);
-        base += (u32)__shfl_sync(0xffffffffu, incl, 31);
-        while (word)
-        {
-            const int b = __ffs(word) - 1;
-            word &= word - 1;
-            const int x = 32 * w + b;
-            // inside flag and record (site position, has-site flag) of the cube vertex k = dx + 2*dy + 4*dz
-            bool in[8], has[8];
-            float4 r[8];
-            int own_id = -1;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
+            const int j = k >> 1, dx = k & 1;
+            in[k] = dx == 0 ? ((W[j] >> b) & 1u) : (b < 31 ? ((W[j] >> (b + 1)) & 1u) : (N[j] & 1u));
+            has[k] = false;
+            r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[k])
             {
-                const int j = k >> 1, dx = k & 1;
-                in[k] = dx == 0 ? ((W[j] >> b) & 1u) : (b < 31 ? ((W[j] >> (b + 1)) & 1u) : (N[j] & 1u));
-                has[k] = false;
-                r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (in[k])
+                const int sid = __ldg(id + (size_t)(x + dx) + (size_t)nx * (size_t)(y + ((k >> 1) & 1)) +
+                                      plane * (size_t)(z + (k >> 2) - z0));
+                if (k == 0)
+                    own_id = sid;
+                if (sid >= 0)
                 {
-                    const int sid = __ldg(id + (size_t)(x + dx) + (size_t)nx * (size_t)(y + ((k >> 1) & 1)) +
-                                          plane * (size_t)(z + (k >> 2) - z0));
-                    if (k == 0)
-                        own_id = sid;
-                    if (sid >= 0)
-                    {
-                        r[k] = __ldg(site + sid);
-                        has[k] = true;
-                    }
+                    r[k] = __ldg(site + sid);
+                    has[k] = true;
                 }
             }
-            auto e2 = [&](int a, int c) -> float { return (has[a] && has[c]) ? vc_dist2f_c(r[a], r[c]) : 0.0f; };
-            // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
-            const float ex0 = e2(0, 1), ex1 = e2(2, 3), ex2 = e2(4, 5), ex3 = e2(6, 7);
-            const float ey0 = e2(0, 2), ey1 = e2(1, 3), ey2 = e2(4, 6), ey3 = e2(5, 7);
-            const float z0e = e2(0, 4), z1e = e2(1, 5), z2e = e2(2, 6), z3e = e2(3, 7);
-            float l[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (in[1])
-                l[0] = __fsqrt_rn(ex0);
-            if (in[2])
-                l[1] = __fsqrt_rn(ey0);
-            if (in[4])
-                l[2] = __fsqrt_rn(z0e);
-            if (in[1] && in[2] && in[3])
-                l[3] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1)));
-            if (in[1] && in[4] && in[5])
-                l[4] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex2), fmaxf(z0e, z1e)));
-            if (in[2] && in[4] && in[6])
-                l[5] = __fsqrt_rn(fmaxf(fmaxf(ey0, ey2), fmaxf(z0e, z2e)));
-            if (in[1] && in[2] && in[3] && in[4] && in[5] && in[6] && in[7])
-            {
-                float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
-                l[6] = __fsqrt_rn(fmaxf(m, fmaxf(fmaxf(z0e, z1e), fmaxf(z2e, z3e))));
-            }
-            const size_t v = row * (size_t)nx + (size_t)x;
-            const u32 q = __ldg(d2 + v);
-            float rad = 0.0f;
-            if (radius_from_d2 && q < (1u << 24))
-                rad = __fsqrt_rn(__fmul_rn((float)q, 0.25f));
-            else if (own_id >= 0)
-                rad = __fsqrt_rn(vc_dist2f_c(r[0], make_float4((float)x, (float)y, (float)z, 0.f)));
-            cvert[pos] = (u32)v;
-            cid[pos] = own_id;
-            cd2[pos] = q;
-#pragma unroll
-            for (int k = 0; k < 7; ++k)
-                clam[(size_t)k * cap + pos] = l[k];
-            crad[pos] = rad;
-            ++pos;
         }
+        auto e2 = [&](int a, int c) -> float { return (has[a] && has[c]) ? vc_dist2f_c(r[a], r[c]) : 0.0f; };
+        // x edges {0,1},{2,3},{4,5},{6,7}; y edges {0,2},{1,3},{4,6},{5,7}; z edges {0,4},{1,5},{2,6},{3,7}
+        const float ex0 = e2(0, 1), ex1 = e2(2, 3), ex2 = e2(4, 5), ex3 = e2(6, 7);
+        const float ey0 = e2(0, 2), ey1 = e2(1, 3), ey2 = e2(4, 6), ey3 = e2(5, 7);
+        const float z0e = e2(0, 4), z1e = e2(1, 5), z2e = e2(2, 6), z3e = e2(3, 7);
+        float l[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (in[1])
+            l[0] = __fsqrt_rn(ex0);
+        if (in[2])
+            l[1] = __fsqrt_rn(ey0);
+        if (in[4])
+            l[2] = __fsqrt_rn(z0e);
+        if (in[1] && in[2] && in[3])
+            l[3] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex1), fmaxf(ey0, ey1)));
+        if (in[1] && in[4] && in[5])
+            l[4] = __fsqrt_rn(fmaxf(fmaxf(ex0, ex2), fmaxf(z0e, z1e)));
+        if (in[2] && in[4] && in[6])
+            l[5] = __fsqrt_rn(fmaxf(fmaxf(ey0, ey2), fmaxf(z0e, z2e)));
+        if (in[1] && in[2] && in[3] && in[4] && in[5] && in[6] && in[7])
+        {
+            float m = fmaxf(fmaxf(fmaxf(ex0, ex1), fmaxf(ex2, ex3)), fmaxf(fmaxf(ey0, ey1), fmaxf(ey2, ey3)));
+            l[6] = __fsqrt_rn(fmaxf(m, fmaxf(fmaxf(z0e, z1e), fmaxf(z2e, z3e))));
+        }
+        const size_t v = row * (size_t)nx + (size_t)x;
+        const u32 q = __ldg(d2 + v);
+        float rad = 0.0f;
+        if (radius_from_d2 && q < (1u << 24))
+            rad = __fsqrt_rn(__fmul_rn((float)q, 0.25f));
+        else if (own_id >= 0)
+            rad = __fsqrt_rn(vc_dist2f_c(r[0], make_float4((float)x, (float)y, (float)z, 0.f)));
+        cvert[pos] = (u32)v;
+        cid[pos] = own_id;
+        cd2[pos] = q;
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            clam[(size_t)k * cap + pos] = l[k];
+        crad[pos] = rad;
     }
 }
 
