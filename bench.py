@@ -418,14 +418,16 @@ def run_ours(args):
         n_in = ctx.compact_count()
         cap = n_in + 1024
         wr = nx // 32 + 1
-        cb = {"bits": api.PinnedArray(((z1 - z0) * ny, wr), np.uint32), "vert": api.PinnedArray((cap,), np.uint32),
-              "id": api.PinnedArray((cap,), np.int32), "d2": api.PinnedArray((cap,), np.uint32),
-              "lam": api.PinnedArray((7, cap), np.float32), "rad": api.PinnedArray((cap,), np.float32)}
+        # the record arrays are the rows of ONE pinned 11 x cap block (vert | id | 4d2 | 7 lambda | radius): a z chunk's
+        # records then come back in a single 2-D copy
+        rec = api.PinnedArray((11, cap), np.uint32)
+        cb = {"bits": api.PinnedArray(((z1 - z0) * ny, wr), np.uint32), "vert": rec.array[0], "id": rec.array[1].view(np.int32),
+              "d2": rec.array[2], "lam": rec.array[3:10].view(np.float32), "rad": rec.array[10].view(np.float32)}
 
         def step_compact(dense=None):
             # on a slab ctx the same call uploads the rank's planes and exchanges the site records over peer memory
-            return ctx.run_dense_host_compact(pin_vol.array, cap, cb["bits"].array, cb["vert"].array, cb["id"].array, cb["d2"].array,
-                                              cb["lam"].array, cb["rad"].array, *(dense or (None, None)))
+            return ctx.run_dense_host_compact(pin_vol.array, cap, cb["bits"].array, cb["vert"], cb["id"], cb["d2"], cb["lam"], cb["rad"],
+                                              *(dense or (None, None)))
 
         e2e_s = time_e2e(step_compact)
         (d2h,) = total(int(cb["bits"].array.nbytes + n_in * 44))
@@ -436,8 +438,8 @@ def run_ours(args):
         ctx.synchronize()
         ids_dev = ctx.download(api.ARR_ID).ravel()
         cube_dev = ctx.download(api.ARR_CUBE).ravel()
-        v = cb["vert"].array[:got_n]
-        if got_n != n_in or not (np.array_equal(cb["id"].array[:got_n], ids_dev[v]) and np.array_equal(cb["lam"].array[6, :got_n], cube_dev[v])):
+        v = cb["vert"][:got_n]
+        if got_n != n_in or not (np.array_equal(cb["id"][:got_n], ids_dev[v]) and np.array_equal(cb["lam"][6, :got_n], cube_dev[v])):
             raise SystemExit("compact e2e records disagree with the dense planes")
         del ids_dev, cube_dev
         e2e_variants["compact"] = {"value": nv_total / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

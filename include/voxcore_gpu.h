@@ -245,7 +245,9 @@ int vc_run_dense_host(vc_ctx* ctx, const float* vol, uint8_t* inside, int32_t* i
  *                       inside the call: upload classified chunk by chunk as it lands, records of a
  *                       z chunk copied back while the next chunk computes.  inside_bits (nullable):
  *                       uint32 [nz*ny][nx/32+1], bit x&31 of word x>>5.  id_dense / d2x4_dense
- *                       (nullable): the full planes as well.  cap < count -> VC_ERR_NOMEM with the
+ *                       (nullable): the full planes as well.  When vert, id, d2x4, lambda7, radius are the
+ *                       rows 0, 1, 2, 3..9, 10 of ONE 11 x cap block of 32-bit words, a chunk's records
+ *                       travel in a single copy.  cap < count -> VC_ERR_NOMEM with the
  *                       count in *n_inside.  On a slab ctx (one rank of a peer group, vc_peer_open):
  *                       vol = the slab's resident planes [max(z0-1,0), min(z1+1,nz)), outputs cover the
  *                       owned planes, the site records travel through the peer exchange, and every rank

@@ -161,6 +161,11 @@ def test_run_dense_host_compact_matches(ctx, fam, n, workers, zchunk, mode):
         o_sites = ob.extract_sites(ob.classify_grid(vol))
         o_ids, o_d2 = ob.closest_grid(o_sites, nx, ny, nz)
         assert np.array_equal(idd, o_ids) and np.array_equal(d2d, o_d2)
+    # record arrays that are the rows of one 11 x cap block take the single-copy path
+    blk = np.empty((11, cap), np.uint32)
+    n_in, ns = ctx.run_dense_host_compact(vol, cap, bits, blk[0], blk[1].view(np.int32), blk[2], blk[3:10].view(np.float32),
+                                          blk[10].view(np.float32))
+    _check_compact(vol, n_in, ns, bits, blk[0], blk[1].view(np.int32), blk[2], blk[3:10].view(np.float32), blk[10].view(np.float32))
     if mode == 2:  # the dense float planes were not produced by that call, and the ABI says so
         with pytest.raises(api.VoxcoreError, match="not computed"):
             ctx.download(api.ARR_CUBE)

@@ -251,18 +251,21 @@ static int compact_prefix_async(vc_ctx* c, u32* host_P)
     return VC_OK;
 }
 
+// device records: ONE block of 11 rows x ccap words -- vert | id | d2x4 | lambda 0..6 | radius -- so that a caller
+// whose host arrays are the rows of one such block gets a z chunk's records in a single 2-D copy
 static int compact_alloc(vc_ctx* c, int64_t n, bool want_radius)
 {
+    (void)want_radius;
     const size_t m = (size_t)(n > 0 ? n : 1);
-    VC_CUDA(c, c->cvert.ensure(m * 4));
-    VC_CUDA(c, c->cid.ensure(m * 4));
-    VC_CUDA(c, c->cd2.ensure(m * 4));
-    VC_CUDA(c, c->clam.ensure(m * 28));
-    if (want_radius)
-        VC_CUDA(c, c->crad.ensure(m * 4));
+    VC_CUDA(c, c->crec.ensure(m * 11 * 4));
     c->ccap = (int64_t)m;
     return VC_OK;
 }
+static inline u32* rec_vert(vc_ctx* c) { return c->crec.as<u32>(); }
+static inline int* rec_id(vc_ctx* c) { return (int*)(c->crec.as<u32>() + (size_t)c->ccap); }
+static inline u32* rec_d2(vc_ctx* c) { return c->crec.as<u32>() + 2 * (size_t)c->ccap; }
+static inline float* rec_lam(vc_ctx* c) { return (float*)(c->crec.as<u32>() + 3 * (size_t)c->ccap); }
+static inline float* rec_rad(vc_ctx* c) { return (float*)(c->crec.as<u32>() + 10 * (size_t)c->ccap); }
 
 // records of the owned planes [za, zb) on stream c->cur (needs the row prefix and the dense planes)
 static int compact_range(vc_ctx* c, int za, int zb, bool want_radius)
@@ -272,8 +275,7 @@ static int compact_range(vc_ctx* c, int za, int zb, bool want_radius)
     VC_LAUNCH(c, "compact_records", k_compact_records, vc_blocks((r1 - r0) * 32, 256), 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
               r0, r1, (size_t)(c->z0 - c->zlo) * c->ny, c->rowpre.as<u32>(), nv, c->id.as<int>(), c->d2.as<u32>(),
               c->edge3.as<float>(), c->face3.as<float>(), c->cube.as<float>(), want_radius ? c->radius.as<float>() : nullptr,
-              (size_t)c->ccap, c->cvert.as<u32>(), c->cid.as<int>(), c->cd2.as<u32>(), c->clam.as<float>(),
-              want_radius ? c->crad.as<float>() : nullptr);
+              (size_t)c->ccap, rec_vert(c), rec_id(c), rec_d2(c), rec_lam(c), want_radius ? rec_rad(c) : nullptr);
     VC_CUDA(c, cudaGetLastError());
     return VC_OK;
 }
@@ -284,8 +286,7 @@ static int sparse_range(vc_ctx* c, int za, int zb)
     const size_t r0 = (size_t)(za - c->z0) * c->ny, r1 = (size_t)(zb - c->z0) * c->ny;
     VC_LAUNCH(c, "sparse_records", k_sparse_records, vc_blocks((r1 - r0) * 32, 256), 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
               c->z0, c->zc, c->zlo, r0, r1, c->rowpre.as<u32>(), c->id.as<int>(), c->d2.as<u32>(), c->site_xyz.as<float4>(),
-              c->lattice ? 1 : 0, (size_t)c->ccap, c->cvert.as<u32>(), c->cid.as<int>(), c->cd2.as<u32>(), c->clam.as<float>(),
-              c->crad.as<float>());
+              c->lattice ? 1 : 0, (size_t)c->ccap, rec_vert(c), rec_id(c), rec_d2(c), rec_lam(c), rec_rad(c));
     VC_CUDA(c, cudaGetLastError());
     return VC_OK;
 }
@@ -297,17 +298,24 @@ static int compact_copy_out(vc_ctx* c, cudaStream_t s, size_t a, size_t b, int64
     if (b <= a)
         return VC_OK;
     const size_t n = b - a;
+    const size_t hc = (size_t)cap;
+    if (vert && id && d2x4 && lambda7 && radius && (uint32_t*)id == vert + hc && d2x4 == vert + 2 * hc &&
+        (uint32_t*)lambda7 == vert + 3 * hc && (uint32_t*)radius == vert + 10 * hc)
+    { // the caller's arrays are the rows of one 11 x cap block: one copy instead of five
+        VC_CUDA(c, cudaMemcpy2DAsync(vert + a, hc * 4, rec_vert(c) + a, (size_t)c->ccap * 4, n * 4, 11, cudaMemcpyDefault, s));
+        return VC_OK;
+    }
     if (vert)
-        VC_CUDA(c, cudaMemcpyAsync(vert + a, c->cvert.as<u32>() + a, n * 4, cudaMemcpyDefault, s));
+        VC_CUDA(c, cudaMemcpyAsync(vert + a, rec_vert(c) + a, n * 4, cudaMemcpyDefault, s));
     if (id)
-        VC_CUDA(c, cudaMemcpyAsync(id + a, c->cid.as<int>() + a, n * 4, cudaMemcpyDefault, s));
+        VC_CUDA(c, cudaMemcpyAsync(id + a, rec_id(c) + a, n * 4, cudaMemcpyDefault, s));
     if (d2x4)
-        VC_CUDA(c, cudaMemcpyAsync(d2x4 + a, c->cd2.as<u32>() + a, n * 4, cudaMemcpyDefault, s));
+        VC_CUDA(c, cudaMemcpyAsync(d2x4 + a, rec_d2(c) + a, n * 4, cudaMemcpyDefault, s));
     if (lambda7)
-        VC_CUDA(c, cudaMemcpy2DAsync(lambda7 + a, (size_t)cap * 4, c->clam.as<float>() + a, (size_t)c->ccap * 4, n * 4, 7,
+        VC_CUDA(c, cudaMemcpy2DAsync(lambda7 + a, (size_t)cap * 4, rec_lam(c) + a, (size_t)c->ccap * 4, n * 4, 7,
                                      cudaMemcpyDefault, s));
     if (radius)
-        VC_CUDA(c, cudaMemcpyAsync(radius + a, c->crad.as<float>() + a, n * 4, cudaMemcpyDefault, s));
+        VC_CUDA(c, cudaMemcpyAsync(radius + a, rec_rad(c) + a, n * 4, cudaMemcpyDefault, s));
     return VC_OK;
 }
 

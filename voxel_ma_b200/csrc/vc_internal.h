@@ -114,7 +114,7 @@ struct vc_ctx
     DevBuf peer_rx, peer_all; // own receive buffer; gathered (keys | corners) of all ranks
     // compact product (vc_compact.cu): exclusive prefix of the inside count per bit row of the owned planes,
     // records of the inside vertices; chunk_hook runs after the measures of each z chunk of the pipeline
-    DevBuf rowpre, cvert, cid, cd2, clam, crad;
+    DevBuf rowpre, crec;
     int64_t ninside = -1, ccap = 0;
     std::function<int(int, int)> chunk_hook;
     int compact_mode = 0;             // 0 automatic, 1 dense planes + gather, 2 records computed directly
