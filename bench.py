@@ -360,6 +360,17 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = nv_total / (ms_per_step * 1e-3)
 
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_per_step,
+                              "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world},
+                              "kernels": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                              "ms_per_step_profiled": ms_prof / args.steps, "e2e": None, "note": "--no-e2e: device-resident legs only"}))
+        ctx.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
     s = (z1 - z0, ny, nx)
     outs = {
@@ -527,6 +538,8 @@ def main():
     ap.add_argument("--workload", default=None, help="sphere256 | torus256 | twist512 | assembly1024 ...")
     ap.add_argument("--grid", default=None, help="NX,NY,NZ (assembly family)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (very large grids: the all-planes leg needs "
+                    "41 B of pinned host memory per grid vertex)")
     ap.add_argument("--exchange", default="peers", choices=["peers", "nccl"],
                     help="N>1: how the site records travel between ranks (peer-memory kernel stores, or NCCL all-gather)")
     args = ap.parse_args()
