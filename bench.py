@@ -352,6 +352,9 @@ def run_ours(args):
     ms_prof = p0.elapsed_time(p1)
     prof = ctx.profile_report()
     ctx.profile(False)
+    if os.environ.get("VC_BENCH_RANKS"):  # development aid: every rank's own kernel times (load balance across slabs)
+        print(f"[rank {rank}] ms/step {ms / args.steps:.3f} profiled {ms_prof / args.steps:.3f} " +
+              " ".join(f"{k}={v['ms'] / args.steps:.3f}" for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]), file=sys.stderr)
     clocks = sampler.stop() if sampler else None
     if dist is not None:
         t = torch.tensor([ms, ms_prof], dtype=torch.float64, device="cuda")
