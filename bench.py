@@ -521,6 +521,32 @@ def run_ours(args):
             "kernels": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
             "ms_per_step_profiled": ms_prof / steps,
         }
+        if world == 1 and fam == "twist":
+            # stage 1' (new functionality, no reference counterpart): the same pass starting from the closed triangle
+            # mesh of the twisted plate instead of a voxel volume -- parity classification, then sites / closest / measures
+            try:
+                from voxel_ma_b200 import synth
+                mv, mt = synth.twist_mesh(nx)
+                ctx.classify_mesh(mv, mt, fetch=False)
+                ctx.run_dense()
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    ctx.classify_mesh(mv, mt, fetch=False)
+                    ns_mesh = ctx.run_dense()
+                    ts.append(time.perf_counter() - t0)
+                mprof = {}
+                ctx.profile(True)
+                ctx.profile_reset()
+                ctx.classify_mesh(mv, mt, fetch=False)
+                mprof = {k: round(v["ms"], 4) for k, v in ctx.profile_report().items() if k.startswith("mesh_")}
+                ctx.profile(False)
+                line["mesh_path"] = {"ms_per_step": float(np.median(ts)) * 1e3, "value": nv_total / float(np.median(ts)), "unit": UNIT,
+                                     "triangles": int(len(mt)), "sites": int(ns_mesh), "classify_kernels_ms": mprof,
+                                     "note": "vc_classify_mesh (warp-ballot parity over the surface triangles, mesh uploaded from the host "
+                                             "each step) + sites + closest + measures; wall clock per step"}
+            except Exception as ex:
+                line["mesh_path"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 with quiet_stdout():

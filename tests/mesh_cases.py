@@ -17,6 +17,8 @@ def mesh_cases():
         # mesh larger than the grid on every side (clipping of rows, columns and the crossing count)
         "box_outside": (*synth.box_mesh((-9.25, -7.5, -3), (50.75, 30.5, 40)), (23, 14, 11), None),
         "sphere_clipped": (*synth.sphere_mesh(32, radius=22.0), (32, 20, 27), None),
+        # faces whose (y,z) boxes hold more than 1024 columns: the block-per-triangle kernel (k_mesh_large)
+        "box_big": (*synth.box_mesh((3.3, 2.2, 1.1), (60.5, 45.5, 38.5)), (64, 48, 40), None),
     }
     # two overlapping solids: even-odd rule (the overlap is outside)
     v1, t1 = synth.sphere_mesh(36, radius=9.0, center=(14.2, 17.1, 18.3))

@@ -17,7 +17,8 @@
 // Two kernels:
 //   k_mesh_toggles   one lane per triangle for the setup; triangles whose (y,z) box holds only a few
 //                    columns are finished by their own lane, the large ones are elected with a warp
-//                    ballot and rasterised by all 32 lanes.  Each crossing is one atomicXor of bit T
+//                    ballot and rasterised by all 32 lanes, the very large ones are queued for
+//                    k_mesh_large (one block each).  Each crossing is one atomicXor of bit T
 //                    in the toggle row of its column (rows of nx+1 bits, the layout of ctx->bits).
 //   k_mesh_parity    one warp per row: inside(i) = parity of the toggles above i = an exclusive
 //                    suffix XOR -- inside a word by shifts, across the words of the row by a warp
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(256) k_mesh_quantise(const float* __restrict__
         atomicOr(flags, 1);
 }
 
-#define MESH_SMALL 6 // columns a lane finishes on its own before the warp takes the large triangles
+#define MESH_SMALL 6   // columns a lane finishes on its own before the warp takes the large triangles
+#define MESH_HUGE 1024 // columns beyond which a triangle gets a whole block (k_mesh_large)
 
 struct TriSetup
 {
@@ -74,7 +76,7 @@ __device__ __forceinline__ void mesh_column(const TriSetup& t, int j, int k, int
 
 __global__ void __launch_bounds__(256) k_mesh_toggles(const int* __restrict__ q, const u32* __restrict__ tris, int64_t nt, int64_t nv,
                                                       int nx, int ny, int zlo, int zhi, int wr, u32* __restrict__ tog,
-                                                      int* __restrict__ flags)
+                                                      int* __restrict__ flags, u32* __restrict__ big_list, u32* __restrict__ nbig)
 {
     const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -102,8 +104,13 @@ __global__ void __launch_bounds__(256) k_mesh_toggles(const int* __restrict__ q,
         for (int k = t.k0; k <= t.k1; ++k)
             for (int j = t.j0; j <= t.j1; ++j)
                 mesh_column(t, j, k, nx, ny, zlo, wr, tog);
+    // triangles whose column box holds more than a warp's worth of work are queued for k_mesh_large, which gives each a
+    // whole block (a mesh of few, large triangles would otherwise leave most of the GPU idle: 2052 triangles = 65 warps)
+    const bool huge = large && (long)nj * nk > MESH_HUGE;
+    if (huge)
+        big_list[atomicAdd(nbig, 1u)] = (u32)ti;
     // large triangles: one at a time, the whole warp over its column box
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, large);
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, large && !huge);
     while (todo)
     {
         const int src = __ffs(todo) - 1;
@@ -120,6 +127,32 @@ __global__ void __launch_bounds__(256) k_mesh_toggles(const int* __restrict__ q,
         {
             const int k = s.k0 + (int)(p / w), j = s.j0 + (int)(p % w);
             mesh_column(s, j, k, nx, ny, zlo, wr, tog);
+        }
+    }
+}
+
+// the queued triangles: one block per triangle (block-stride over the queue), all threads over its column box
+__global__ void __launch_bounds__(256) k_mesh_large(const int* __restrict__ q, const u32* __restrict__ tris, const u32* __restrict__ big_list,
+                                                    const u32* __restrict__ nbig, int nx, int ny, int zlo, int zhi, int wr,
+                                                    u32* __restrict__ tog)
+{
+    const u32 n = *nbig;
+    for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x)
+    {
+        const int64_t ti = big_list[idx];
+        const u32 ia = tris[3 * ti], ib = tris[3 * ti + 1], ic = tris[3 * ti + 2]; // indices were validated when queued
+        TriSetup t;
+        t.ax = q[3 * ia], t.ay = q[3 * ia + 1], t.az = q[3 * ia + 2];
+        t.bx = q[3 * ib], t.by = q[3 * ib + 1], t.bz = q[3 * ib + 2];
+        t.cx = q[3 * ic], t.cy = q[3 * ic + 1], t.cz = q[3 * ic + 2];
+        vc_mesh_orient_ccw(&t.ax, &t.ay, &t.az, &t.bx, &t.by, &t.bz, &t.cx, &t.cy, &t.cz);
+        vc_mesh_columns(t.ay, t.az, t.by, t.bz, t.cy, t.cz, ny, zlo, zhi, &t.j0, &t.j1, &t.k0, &t.k1);
+        const int w = t.j1 - t.j0 + 1;
+        const long total = (long)w * (t.k1 - t.k0 + 1);
+        for (long p = threadIdx.x; p < total; p += blockDim.x)
+        {
+            const int k = t.k0 + (int)(p / w), j = t.j0 + (int)(p % w);
+            mesh_column(t, j, k, nx, ny, zlo, wr, tog);
         }
     }
 }
@@ -200,8 +233,8 @@ int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* 
     VC_CUDA(c, c->bits.ensure(nrows * (size_t)c->wr * 4 + 16));
     VC_CUDA(c, c->scratch.ensure(256));
     VC_CUDA(c, cudaMemsetAsync(c->bits.p, 0, nrows * (size_t)c->wr * 4, c->stream));
-    VC_CUDA(c, cudaMemsetAsync(c->scratch.p, 0, 8, c->stream));
-    DevBuf dv, dq, dt;
+    VC_CUDA(c, cudaMemsetAsync(c->scratch.p, 0, 80, c->stream)); // flags at [0], the queue length of k_mesh_large at byte 64
+    DevBuf dv, dq, dt, dl;
     cudaError_t e = cudaSuccess;
     const float* pv = verts;
     const u32* pt = tris;
@@ -219,6 +252,8 @@ int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* 
     }
     if (e == cudaSuccess)
         e = dq.ensure((size_t)(nv > 0 ? nv : 1) * 12);
+    if (e == cudaSuccess)
+        e = dl.ensure((size_t)(nt > 0 ? nt : 1) * 4);
     int flags = 0;
     if (e == cudaSuccess)
     {
@@ -226,8 +261,13 @@ int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* 
         if (nv > 0)
             VC_LAUNCH(c, "mesh_quantise", k_mesh_quantise, vc_blocks((size_t)nv, 256), 256, 0, pv, nv, xf, dq.as<int>(), dflags);
         if (nt > 0 && nv > 0)
+        {
+            u32* nbig = (u32*)c->scratch.p + 16;
             VC_LAUNCH(c, "mesh_toggles", k_mesh_toggles, vc_blocks((size_t)nt, 256), 256, 0, dq.as<int>(), pt, nt, nv, c->nx, c->ny,
-                      c->zlo, c->zhi, c->wr, c->bits.as<u32>(), dflags);
+                      c->zlo, c->zhi, c->wr, c->bits.as<u32>(), dflags, dl.as<u32>(), nbig);
+            VC_LAUNCH(c, "mesh_large", k_mesh_large, c->sm_count * 8, 256, 0, dq.as<int>(), pt, dl.as<u32>(), nbig, c->nx, c->ny, c->zlo,
+                      c->zhi, c->wr, c->bits.as<u32>());
+        }
         VC_LAUNCH(c, "mesh_parity", k_mesh_parity, vc_blocks(nrows * 32, 256), 256, 0, c->bits.as<u32>(), c->inside.as<u8>(), nrows,
                   c->nx, c->wr);
         e = cudaMemcpyAsync(&flags, dflags, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
@@ -239,6 +279,7 @@ int st_classify_mesh(vc_ctx* c, const float* verts, int64_t nv, const uint32_t* 
     dv.release();
     dq.release();
     dt.release();
+    dl.release();
     if (e != cudaSuccess)
         return vc_fail(c, VC_ERR_CUDA, "vc_classify_mesh", e);
     if (flags & 2)
