@@ -459,6 +459,23 @@ def run_ours(args):
         e2e_variants["compact"] = {"value": nv_total / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "inside_vertices": n_in_total,
                                    "result": "occupancy bit rows + (vertex u32, id i32, 4d2 u32, 7 lambda f32, radius f32) per inside vertex"}
+        if world == 1:
+            # the same pass from an MRC mode 0 (signed byte) volume -- a format the reference's reader takes as well
+            # (isosurface_tao/reader.h:235-239); the synthetic field is quantised to 1/16, which moves the surface a
+            # little, so this is another volume, timed for what the narrower upload buys
+            v8 = api.PinnedArray(pin_vol.array.shape, np.int8)
+            v8.array[...] = np.clip(np.rint(pin_vol.array * 16.0), -127, 127).astype(np.int8)
+            ctx.upload_volume(v8.array)
+            ctx.classify_grid(fetch=False)
+            cap8 = ctx.compact_count() + 1024
+            rec8 = api.PinnedArray((11, cap8), np.uint32)
+            dt8 = time_e2e(lambda: ctx.run_dense_host_compact(v8.array, cap8, cb["bits"].array, rec8.array[0], rec8.array[1].view(np.int32),
+                                                              rec8.array[2], rec8.array[3:10].view(np.float32),
+                                                              rec8.array[10].view(np.float32)))
+            e2e_variants["compact_int8_volume"] = {"value": nv_total / dt8, "ms_per_step": dt8 * 1e3, "h2d_bytes_per_step": int(v8.array.nbytes),
+                                                   "d2h_bytes_per_step": int(cb["bits"].array.nbytes + (cap8 - 1024) * 44),
+                                                   "result": "compact product from an MRC mode 0 (int8) volume (field quantised to 1/16)"}
+            del v8, rec8
         dense = (api.PinnedArray((z1 - z0, ny, nx), np.int32), api.PinnedArray((z1 - z0, ny, nx), np.uint32))
         dt = time_e2e(lambda: step_compact((dense[0].array, dense[1].array)))
         e2e_variants["compact_plus_dense_ids"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,

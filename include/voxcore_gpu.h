@@ -64,6 +64,9 @@ int vc_set_grid(vc_ctx* ctx, int nx, int ny, int nz, int z0, int z1);
  * Must cover [max(z0-1,0), min(z1+1,nz)) -- one halo plane each side of the slab.
  * planes: host or device. */
 int vc_volume_upload_f32(vc_ctx* ctx, const float* planes, int zlo, int zhi);
+/* The same for an MRC mode 0 payload (signed bytes, x fastest): the reference's reader widens them to double
+ * exactly like the float ones (3rdparty/isosurface_tao/reader.h:235-239), so inside <=> value > 0. */
+int vc_volume_upload_i8(vc_ctx* ctx, const int8_t* planes, int zlo, int zhi);
 /* whole volume in Tao's in-memory order double[x*ny*nz + y*nz + z] (volume.h:217-224);
  * requires the ctx to own the whole grid. */
 int vc_volume_upload_f64_zfast(vc_ctx* ctx, const double* vol);
@@ -263,6 +266,10 @@ int vc_compact_records(vc_ctx* ctx, int64_t cap, uint32_t* vert, int32_t* id, ui
 int vc_run_dense_host_compact(vc_ctx* ctx, const float* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
                               uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
                               uint32_t* d2x4_dense, int64_t* nsites);
+/* the same call for an MRC mode 0 (signed byte) host volume: a quarter of the bytes cross the bus */
+int vc_run_dense_host_compact_i8(vc_ctx* ctx, const int8_t* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
+                                 uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
+                                 uint32_t* d2x4_dense, int64_t* nsites);
 
 /* ---- instrumentation --------------------------------------------------------------------------------
  * The reference's only instrumentation is struct timer around stages (include/commondefs.h:110-168);

@@ -587,3 +587,35 @@ def test_closest_points_f32_general_sites(ctx):
         oi, od2 = ob.closest_points_f32(pts, q, lim)
         assert np.array_equal(idx, oi) and np.array_equal(d2, od2)
     assert (d2[-50:] == 0).all()
+
+
+# ---- MRC mode 0 volumes (signed bytes) ---------------------------------------------------------------
+def _as_i8(vol):
+    return np.clip(np.rint(vol * 16.0), -127, 127).astype(np.int8)
+
+
+@pytest.mark.parametrize("fam,n", [("twist", 64), ("assembly", 33), ("sphere", 40), ("torus", 96)])
+def test_int8_volume_classify_and_pipeline(ctx, fam, n):
+    """vc_volume_upload_i8 / vc_run_dense_host_compact_i8: the byte volume classifies like the same values as floats"""
+    v8 = _as_i8(synth.make(fam, n))
+    vf = v8.astype(np.float32)
+    nz, ny, nx = v8.shape
+    o_inside = ob.classify_grid(vf)
+    ctx.set_grid(nx, ny, nz)
+    ctx.upload_volume(v8)
+    assert np.array_equal(ctx.classify_grid(), o_inside)
+    assert ctx.extract_sites() == len(ob.extract_sites(o_inside))
+    cap = int(o_inside.sum()) + 3
+    bits = np.empty((nz * ny, nx // 32 + 1), np.uint32)
+    vert, ids, d2 = np.empty(cap, np.uint32), np.empty(cap, np.int32), np.empty(cap, np.uint32)
+    lam, rad = np.empty((7, cap), np.float32), np.empty(cap, np.float32)
+    n_in, ns = ctx.run_dense_host_compact(v8, cap, bits, vert, ids, d2, lam, rad)
+    _check_compact(vf, n_in, ns, bits, vert, ids, d2, lam, rad)
+
+
+def test_int8_volume_sign_edge_values(ctx):
+    v8 = np.zeros((5, 7, 64), np.int8)
+    v8[1:4, 2:5, 10:50] = np.array([-128, -1, 0, 1, 127], np.int8)[np.arange(40) % 5][None, None, :]
+    ctx.set_grid(64, 7, 5)
+    ctx.upload_volume(v8)
+    assert np.array_equal(ctx.classify_grid(), (v8 > 0).astype(np.uint8))

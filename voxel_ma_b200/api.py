@@ -21,13 +21,13 @@ ARR_INSIDE, ARR_ID, ARR_D2X4, ARR_EDGE3, ARR_FACE3, ARR_CUBE, ARR_RADIUS = range
 # every symbol include/voxcore_gpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vc_abi_version", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
-    "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_f64_zfast",
+    "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_i8", "vc_volume_upload_f64_zfast",
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
     "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_closest_points_f32", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
-    "vc_run_dense_host_compact", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
+    "vc_run_dense_host_compact", "vc_run_dense_host_compact_i8", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
 
@@ -89,6 +89,8 @@ def load_library(path: str | None = None):
     lib.vc_compact_count.argtypes = [vp, C.POINTER(i64)]
     lib.vc_compact_records.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.vc_run_dense_host_compact.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.vc_run_dense_host_compact_i8.argtypes = [vp, vp, vp, i64, C.POINTER(i64), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.vc_volume_upload_i8.argtypes = [vp, vp, i32, i32]
     lib.vc_closest_grid.argtypes = [vp, vp, vp]
     lib.vc_closest_points.argtypes = [vp, vp, i64, vp, vp]
     lib.vc_closest_points_f32.argtypes = [vp, vp, i64, C.c_float, vp, vp]
@@ -192,12 +194,15 @@ class Context:
         return (self.z1 - self.z0, self.ny, self.nx)
 
     def upload_volume(self, vol: np.ndarray, zlo: int = 0):
-        """vol[z,y,x] float32 planes starting at global plane zlo (whole volume: zlo=0)."""
-        v = np.ascontiguousarray(vol, np.float32)
+        """vol[z,y,x] planes starting at global plane zlo (whole volume: zlo=0): float32 (MRC mode 2), or int8 as it is
+        (MRC mode 0)."""
+        i8 = vol.dtype == np.int8
+        v = np.ascontiguousarray(vol, np.int8 if i8 else np.float32)
         if not self.nx:
             nz, ny, nx = v.shape
             self.set_grid(nx, ny, nz)
-        self._ck(self.lib.vc_volume_upload_f32(self.h, _ptr(v), zlo, zlo + v.shape[0]))
+        fn = self.lib.vc_volume_upload_i8 if i8 else self.lib.vc_volume_upload_f32
+        self._ck(fn(self.h, _ptr(v), zlo, zlo + v.shape[0]))
 
     def upload_volume_f64_zfast(self, vol_zfast: np.ndarray, nx, ny, nz):
         self.set_grid(nx, ny, nz)
@@ -431,7 +436,8 @@ class Context:
                                id_dense=None, d2x4_dense=None):
         """-> (n_inside, n_sites).  lambda7 must be laid out [7][cap]."""
         n, ns = C.c_int64(), C.c_int64()
-        self._ck(self.lib.vc_run_dense_host_compact(self.h, _ptr(vol), _ptr(inside_bits), cap, C.byref(n), _ptr(vert), _ptr(ids),
+        fn = self.lib.vc_run_dense_host_compact_i8 if vol.dtype == np.int8 else self.lib.vc_run_dense_host_compact
+        self._ck(fn(self.h, _ptr(vol), _ptr(inside_bits), cap, C.byref(n), _ptr(vert), _ptr(ids),
                                                     _ptr(d2x4), _ptr(lambda7), _ptr(radius), _ptr(id_dense), _ptr(d2x4_dense),
                                                     C.byref(ns)))
         return n.value, ns.value

@@ -219,26 +219,35 @@ extern "C"
         return VC_OK;
     }
 
-    int vc_volume_upload_f32(vc_ctx* c, const float* planes, int zlo, int zhi)
+    static int upload_planes(vc_ctx* c, const void* planes, int zlo, int zhi, bool i8)
     {
         if (!c || !planes)
             return VC_ERR_INVALID;
         if (!c->have_grid)
-            return vc_fail(c, VC_ERR_STATE, "vc_volume_upload_f32: call vc_set_grid first");
+            return vc_fail(c, VC_ERR_STATE, "vc_volume_upload: call vc_set_grid first");
         int need_lo = c->z0 > 0 ? c->z0 - 1 : 0, need_hi = c->z1 < c->nz ? c->z1 + 1 : c->nz;
         if (zlo < 0 || zhi > c->nz || zlo > need_lo || zhi < need_hi)
-            return vc_fail(c, VC_ERR_INVALID, "vc_volume_upload_f32: planes must cover the slab plus one halo plane each side");
+            return vc_fail(c, VC_ERR_INVALID, "vc_volume_upload: planes must cover the slab plus one halo plane each side");
         VC_CUDA(c, cudaSetDevice(c->device));
-        size_t n = (size_t)c->nx * c->ny * (size_t)(zhi - zlo);
-        VC_CUDA(c, c->vol.ensure(n * 4 + 64));
-        VC_CUDA(c, cudaMemcpyAsync(c->vol.p, planes, n * 4, cudaMemcpyDefault, c->stream));
+        const size_t n = (size_t)c->nx * c->ny * (size_t)(zhi - zlo), esz = i8 ? 1 : 4;
+        VC_CUDA(c, c->vol.ensure(n * esz + 64));
+        VC_CUDA(c, cudaMemcpyAsync(c->vol.p, planes, n * esz, cudaMemcpyDefault, c->stream));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         c->zlo = zlo;
         c->zhi = zhi;
+        c->vol_i8 = i8;
         c->have_vol = true;
         c->have_inside = c->have_sites = c->have_closest = c->have_measures = false;
         return VC_OK;
     }
+
+    int vc_volume_upload_i8(vc_ctx* c, const int8_t* planes, int zlo, int zhi) { return upload_planes(c, planes, zlo, zhi, true); }
+
+    int vc_volume_upload_f32(vc_ctx* c, const float* planes, int zlo, int zhi)
+    {
+        return upload_planes(c, planes, zlo, zhi, false);
+    }
+
 
     int vc_volume_upload_f64_zfast(vc_ctx* c, const double* vol)
     {
@@ -644,6 +653,7 @@ extern "C"
         const size_t plane = (size_t)c->nx * c->ny, nv = plane * c->nz;
         VC_CUDA(c, c->vol.ensure(nv * 4 + 64));
         VC_CUDA(c, c->inside.ensure(nv + 16));
+        c->vol_i8 = false;
         c->zlo = 0;
         c->zhi = c->nz;
         // H2D in plane chunks on the copy stream; classification of a chunk starts as soon as it lands

@@ -367,12 +367,13 @@ extern "C"
     //   upload in plane chunks, each classified as it lands -> sites -> per z chunk of the pipeline:
     //   transform, measures, compaction, and the chunk's records start their way back while the next
     //   chunk computes.  One host synchronisation in the middle (site count + inside count).
-    int vc_run_dense_host_compact(vc_ctx* c, const float* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
-                                  uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
-                                  uint32_t* d2x4_dense, int64_t* nsites)
+    static int host_compact(vc_ctx* c, const void* vol, bool i8, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
+                            uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
+                            uint32_t* d2x4_dense, int64_t* nsites)
     {
         if (!c || !vol || cap < 0)
             return VC_ERR_INVALID;
+        const size_t esz = i8 ? 1 : 4; // bytes per voxel of the host volume
         VC_CUDA(c, cudaSetDevice(c->device));
         if (!c->have_grid)
             return vc_fail(c, VC_ERR_STATE, "vc_run_dense_host_compact: call vc_set_grid first");
@@ -383,9 +384,10 @@ extern "C"
         // resident voxel planes: the slab plus one halo plane on each interior side (what vc_volume_upload_f32 takes)
         const int zlo = c->z0 > 0 ? c->z0 - 1 : 0, zhi = c->z1 < c->nz ? c->z1 + 1 : c->nz;
         const size_t plane = (size_t)c->nx * c->ny, nv = plane * (size_t)(c->z1 - c->z0);
-        VC_CUDA(c, c->vol.ensure(plane * (size_t)(zhi - zlo) * 4 + 64));
+        VC_CUDA(c, c->vol.ensure(plane * (size_t)(zhi - zlo) * esz + 64));
         c->zlo = zlo;
         c->zhi = zhi;
+        c->vol_i8 = i8;
         c->have_vol = true;
         c->have_inside = c->have_sites = c->have_closest = c->have_measures = false;
         const bool trace = getenv("VC_TRACE") != nullptr; // development aid: where the call's time goes
@@ -412,7 +414,7 @@ extern "C"
         {
             const int ze = z + chunk < zhi ? z + chunk : zhi;
             const size_t off = plane * (size_t)(z - zlo), cnt = plane * (size_t)(ze - z);
-            VC_CUDA(c, cudaMemcpyAsync(c->vol.as<float>() + off, vol + off, cnt * 4, cudaMemcpyDefault, c->s_h2d));
+            VC_CUDA(c, cudaMemcpyAsync(c->vol.as<char>() + off * esz, (const char*)vol + off * esz, cnt * esz, cudaMemcpyDefault, c->s_h2d));
             VC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             VC_CUDA(c, cudaEventRecord(ev, c->s_h2d));
             VC_CUDA(c, cudaStreamWaitEvent(c->stream, ev, 0));
@@ -532,5 +534,19 @@ extern "C"
         if (nsites)
             *nsites = c->nsites;
         return VC_OK;
+    }
+
+    int vc_run_dense_host_compact(vc_ctx* c, const float* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
+                                  uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
+                                  uint32_t* d2x4_dense, int64_t* nsites)
+    {
+        return host_compact(c, vol, false, inside_bits, cap, n_inside, vert, id, d2x4, lambda7, radius, id_dense, d2x4_dense, nsites);
+    }
+
+    int vc_run_dense_host_compact_i8(vc_ctx* c, const int8_t* vol, uint32_t* inside_bits, int64_t cap, int64_t* n_inside,
+                                     uint32_t* vert, int32_t* id, uint32_t* d2x4, float* lambda7, float* radius, int32_t* id_dense,
+                                     uint32_t* d2x4_dense, int64_t* nsites)
+    {
+        return host_compact(c, vol, true, inside_bits, cap, n_inside, vert, id, d2x4, lambda7, radius, id_dense, d2x4_dense, nsites);
     }
 }

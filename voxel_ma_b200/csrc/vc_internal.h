@@ -79,6 +79,7 @@ struct vc_ctx
     int nx = 0, ny = 0, nz = 0, z0 = 0, z1 = 0, zc = 0, zlo = 0, zhi = 0;
     bool have_grid = false, have_vol = false, have_inside = false, have_sites = false, have_closest = false,
          have_measures = false;
+    bool vol_i8 = false;        // the resident volume is MRC mode 0 (signed bytes) instead of float32
     bool attr_measures = false; // dynamic shared memory opt-in done for this device
     bool lattice = true; // sites lie on the corner lattice -> dense transform
     DevBuf vol, inside;

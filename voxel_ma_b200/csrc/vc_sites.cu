@@ -57,6 +57,52 @@ __global__ void __launch_bounds__(256)
             inside[i] = vol[i] > 0.0f;
 }
 
+// MRC mode 0 volumes (signed bytes; the reference's reader widens them to double the same way, isosurface_tao/reader.h:
+// 235-239): inside <=> value > 0.  2 B / voxel; a thread takes 16 voxels (128-bit load, 128-bit store of the flags), two
+// neighbouring lanes make one 32-voxel bit word.  PACK needs whole-word rows (nx % 32 == 0).
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+    k_classify_i8(const signed char* __restrict__ vol, u8* __restrict__ inside, u32* __restrict__ bits, size_t n, int words_per_row, int wr)
+{
+    if (PACK)
+    {
+        size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+        const size_t stride = (size_t)gridDim.x * blockDim.x * 16;
+        for (; i + 15 < n; i += stride) // n is a multiple of 32: both lanes of a word take the same trips
+        {
+            const int4 v = __ldcs(reinterpret_cast<const int4*>(vol + i));
+            const u32 in[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+            u32 out[4], half = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+            {
+                u32 o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                {
+                    const u32 f = (signed char)((in[g] >> (8 * b)) & 0xFFu) > 0 ? 1u : 0u;
+                    o |= f << (8 * b);
+                    half |= f << (4 * g + b);
+                }
+                out[g] = o;
+            }
+            *reinterpret_cast<uint4*>(inside + i) = make_uint4(out[0], out[1], out[2], out[3]);
+            const u32 other = __shfl_xor_sync(0xFFFFFFFFu, half, 1);
+            if ((threadIdx.x & 1) == 0)
+            {
+                const size_t wflat = i >> 5, row = wflat / (size_t)words_per_row;
+                bits[row * (size_t)wr + (wflat - row * (size_t)words_per_row)] = half | (other << 16);
+            }
+        }
+    }
+    else
+    {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i < n; i += (size_t)gridDim.x * blockDim.x)
+            inside[i] = vol[i] > 0;
+    }
+}
+
 // Occupancy bit rows from the byte flags, any nx: one thread per word (row, w).
 __global__ void __launch_bounds__(256) k_pack_bits(const u8* __restrict__ inside, u32* __restrict__ bits, size_t nrows, int nx, int wr)
 {
@@ -120,7 +166,10 @@ __global__ void k_classify_f64_zfast(const double* __restrict__ vol, u8* __restr
 // plane chunk while later chunks are still on the wire (vc_compact.cu): st_classify_begin sizes the
 // buffers and clears the pad word of every bit row, st_classify_planes handles voxel planes
 // [za, zb) of the resident range on stream c->cur.
-bool st_classify_chunkable(const vc_ctx* c) { return (c->nx & 31) == 0 || (((size_t)c->nx * c->ny) & 3) == 0; }
+bool st_classify_chunkable(const vc_ctx* c)
+{
+    return (c->nx & 31) == 0 || (c->vol_i8 ? true : (((size_t)c->nx * c->ny) & 3) == 0);
+}
 
 int st_classify_begin(vc_ctx* c)
 {
@@ -143,7 +192,20 @@ int st_classify_planes(vc_ctx* c, int za, int zb)
         return VC_OK;
     size_t want = (n / 4 + 255) / 256 + 1, cap = (size_t)c->sm_count * 16;
     unsigned blocks = (unsigned)(want < cap ? want : cap);
-    if ((c->nx & 31) == 0)
+    if (c->vol_i8)
+    {
+        if ((c->nx & 31) == 0)
+            VC_LAUNCH(c, "classify_i8", k_classify_i8<true>, blocks, 256, 0, c->vol.as<signed char>() + off, c->inside.as<u8>() + off,
+                      c->bits.as<u32>() + row0 * (size_t)c->wr, n, c->nx / 32, c->wr);
+        else
+        {
+            VC_LAUNCH(c, "classify_i8", k_classify_i8<false>, blocks, 256, 0, c->vol.as<signed char>() + off,
+                      c->inside.as<u8>() + off, (u32*)nullptr, n, 0, 0);
+            VC_LAUNCH(c, "pack_bits", k_pack_bits, vc_blocks(nrows * (size_t)c->wr, 256), 256, 0, c->inside.as<u8>() + off,
+                      c->bits.as<u32>() + row0 * (size_t)c->wr, nrows, c->nx, c->wr);
+        }
+    }
+    else if ((c->nx & 31) == 0)
         VC_LAUNCH(c, "classify_f32", k_classify_f32<true>, blocks, 256, 0, c->vol.as<float>() + off, c->inside.as<u8>() + off,
                   c->bits.as<u32>() + row0 * (size_t)c->wr, n, c->nx / 32, c->wr);
     else
