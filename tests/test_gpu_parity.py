@@ -619,3 +619,17 @@ def test_int8_volume_sign_edge_values(ctx):
     ctx.set_grid(64, 7, 5)
     ctx.upload_volume(v8)
     assert np.array_equal(ctx.classify_grid(), (v8 > 0).astype(np.uint8))
+
+
+def test_site_detection_capacity_regrows(ctx_factory):
+    """single-pass site detection: a volume with far more sites than the context has seen before overflows the
+    capacity carried over from the previous call and is detected again with the exact size"""
+    c = ctx_factory()
+    for vol in (synth.sphere(20), synth.torus(96), synth.sphere(20), synth.twist(72)):
+        nz, ny, nx = vol.shape
+        c.set_grid(nx, ny, nz)
+        c.upload_volume(vol)
+        inside = c.classify_grid()
+        o_sites = ob.extract_sites(ob.classify_grid(vol))
+        assert c.extract_sites() == len(o_sites)
+        assert np.array_equal(c.get_sites(), o_sites)

@@ -88,6 +88,7 @@ struct vc_ctx
     // site candidates of this slab (unsorted) and the global, numbered site set
     DevBuf cand_key, cand_corner;
     int64_t ncand = 0;
+    size_t cand_cap_hint = 0; // capacity the next single-pass detection starts with (grows with the counts seen)
     DevBuf site_key, site_corner, site_xyz; // u64, u64, float4 in id order
     int64_t nsites = 0;
     DevBuf line_ptr, line_ent; // z-line lists: int32[(nx+1)(ny+1)+1], u64 (cz<<32|id)

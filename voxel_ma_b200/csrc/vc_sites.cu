@@ -353,8 +353,11 @@ __global__ void __launch_bounds__(256)
                 const u32 rin = (rows_in >> k) & 1u;
                 inb |= ((cx >= 1 ? rin : 0u) << k) | ((cx < nx ? rin : 0u) << (4 + k));
             }
-            keys[pos] = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
-            corners[pos] = vc_pack_corner(cx, cy, cz);
+            if (pos < peers.cap)
+            { // (peers.cap carries the capacity of the local arrays in this mode)
+                keys[pos] = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
+                corners[pos] = vc_pack_corner(cx, cy, cz);
+            }
             ++pos;
         }
         return;
@@ -426,24 +429,36 @@ int st_detect_sites(vc_ctx* c)
     size_t total = (size_t)c->wr * (c->ny + 1) * (size_t)(cze - czb);
     VC_CUDA(c, c->scratch.ensure(256));
     u64* counter = c->scratch.as<u64>();
-    VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
     unsigned blocks = vc_blocks(total, 256);
-    VC_LAUNCH(c, "detect_sites_count", k_detect_sites<0>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny, c->nz,
-              c->zlo, czb, cze, nullptr, nullptr, counter, VcPeerDst());
-    u64 n = 0;
-    VC_CUDA(c, cudaMemcpyAsync(&n, counter, 8, cudaMemcpyDeviceToHost, c->stream));
-    VC_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->ncand = (int64_t)n;
-    VC_CUDA(c, c->cand_key.ensure((n + 1) * 8));
-    VC_CUDA(c, c->cand_corner.ensure((n + 1) * 8));
-    if (n)
+    // One pass: the records are appended into buffers of a capacity chosen beforehand (the last count plus a quarter,
+    // or, the first time, four records per voxel of the three grid faces -- any surface that is not space-filling stays
+    // far below), and the counter says afterwards how many there were.  Only when it says "more than the capacity"
+    // is the pass repeated, now with the exact size: no separate counting pass in front of the host read-back.
+    size_t cap = c->cand_cap_hint;
+    if (cap == 0)
+        cap = 4 * ((size_t)c->nx * c->ny + (size_t)c->ny * (cze - czb) + (size_t)c->nx * (cze - czb)) + 4096;
+    for (int attempt = 0; attempt < 2; ++attempt)
     {
+        VC_CUDA(c, c->cand_key.ensure((cap + 1) * 8));
+        VC_CUDA(c, c->cand_corner.ensure((cap + 1) * 8));
         VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
+        VcPeerDst lim;
+        lim.cap = (u64)cap;
         VC_LAUNCH(c, "detect_sites_emit", k_detect_sites<1>, blocks, 256, 0, c->bits.as<u32>(), c->wr, c->nx, c->ny,
-                  c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter, VcPeerDst());
-        VC_CUDA(c, cudaGetLastError());
+                  c->nz, c->zlo, czb, cze, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), counter, lim);
+        u64 n = 0;
+        VC_CUDA(c, cudaMemcpyAsync(&n, counter, 8, cudaMemcpyDeviceToHost, c->stream));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->ncand = (int64_t)n;
+        if (n <= cap)
+        {
+            const size_t want = (size_t)n + (size_t)n / 4 + 4096;
+            c->cand_cap_hint = want > c->cand_cap_hint ? want : c->cand_cap_hint;
+            return VC_OK;
+        }
+        cap = (size_t)n; // the counter counted everything: the second attempt fits exactly
     }
-    return VC_OK;
+    return vc_fail(c, VC_ERR_STATE, "site detection: record count changed between two passes over the same flags");
 }
 
 // Site detection of this slab's corner planes written straight into every rank's receive region
