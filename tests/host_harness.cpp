@@ -114,6 +114,25 @@ extern "C"
         vc_envelope_line(in, 1L, ncand, ntgt, stk, [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; });
     }
 
+    // the same line with the candidate bitmap pass X uses (vc_edt.cu): bit j set <=> candidate j is live; the entries of
+    // dead candidates are overwritten with garbage first -- the scan must never look at them
+    void hh_envelope_masked(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
+    {
+        std::vector<uint32_t> mask((size_t)(ncand + 31) / 32 + 1, 0u);
+        std::vector<vc_u64> g(in, in + ncand);
+        for (int j = 0; j < ncand; ++j)
+        {
+            if (in[j] != VC_INF)
+                mask[j >> 5] |= 1u << (j & 31);
+            else
+                g[j] = 0x0123456789ABCDEFull * (vc_u64)(j + 1); // what pass Z leaves behind: never-written memory
+        }
+        std::vector<vc_u64> stkv(ncand + 1);
+        vc_stack_array stk{stkv.data()};
+        vc_envelope_line(g.data(), 1L, ncand, ntgt, stk, [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; },
+                         mask.data());
+    }
+
     // (key, corner) records of one z-slab, as vc_sites_detect_local reports them: corner planes
     // [czb,cze) of a grid nx*ny*nz; `inside` holds voxel planes [zlo, zhi). Returns the count.
     int64_t hh_site_records(const uint8_t* inside, int nx, int ny, int nz, int zlo, int zhi, int czb, int cze,

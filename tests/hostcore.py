@@ -54,6 +54,14 @@ def envelope(H, ntgt):
     return out
 
 
+def envelope_masked(H, ntgt):
+    """same line through the candidate-bitmap path of pass X (dead candidates hold garbage)"""
+    H = np.ascontiguousarray(H, np.uint64)
+    out = np.empty(ntgt, np.uint64)
+    lib().hh_envelope_masked(_p(H), len(H), ntgt, _p(out))
+    return out
+
+
 def site_records(inside_planes, nx, ny, nz, zlo, czb, cze):
     ins = np.ascontiguousarray(inside_planes, np.uint8)
     zhi = zlo + ins.shape[0]

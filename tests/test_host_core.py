@@ -53,8 +53,11 @@ def test_envelope_line_random(n, dmax, density):
         H[rng.random(n) > density] = np.uint64(0xFFFFFFFFFFFFFFFF)
         out = hc.envelope(H, n - 1)
         assert np.array_equal(out, _brute_line(H, n - 1))
+        # pass X's form: a bitmap says which candidates exist, the others are never read
+        assert np.array_equal(hc.envelope_masked(H, n - 1), out)
     empty = np.full(n, 0xFFFFFFFFFFFFFFFF, np.uint64)
     assert (hc.envelope(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    assert (hc.envelope_masked(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
 
 
 @pytest.mark.parametrize("n,levels", [(33, 2), (257, 3), (1025, 2), (2049, 4)])
