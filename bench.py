@@ -265,6 +265,18 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     dist = None
     torch.cuda.set_device(local)
+    # stdout must carry ONE line (rank 0's JSON): anything a library prints there meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -365,10 +377,10 @@ def run_ours(args):
 
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_per_step,
-                              "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world},
-                              "kernels": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-                              "ms_per_step_profiled": ms_prof / args.steps, "e2e": None, "note": "--no-e2e: device-resident legs only"}))
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_per_step,
+                  "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world},
+                  "kernels": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                  "ms_per_step_profiled": ms_prof / args.steps, "e2e": None, "note": "--no-e2e: device-resident legs only"})
         ctx.close()
         if dist is not None:
             dist.barrier()
@@ -570,7 +582,7 @@ def run_ours(args):
                     line["cpu_baseline"] = cpu_reference_rate(fam, grid, budget_s=20.0)
             except Exception as ex:  # the checker missing must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
