@@ -55,3 +55,23 @@ def test_slab_site_records_union_equals_whole_grid_sites():
     assert len(np.unique(k)) == len(k) == len(want)
     got = slabs.unpack_corners(c[np.argsort(k)]).astype(np.float32) - 0.5
     assert np.array_equal(got, want)
+
+
+def test_balanced_bounds():
+    from voxel_ma_b200 import slabs
+    rng = np.random.default_rng(3)
+    for nz, world in ((128, 8), (1024, 8), (37, 5), (8, 8), (9, 2)):
+        w = 1.0 + 5.0 * rng.random(nz) * (np.arange(nz) > nz // 3)
+        b = slabs.balanced_bounds(w, world)
+        assert b[0][0] == 0 and b[-1][1] == nz and all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(z1 > z0 for z0, z1 in b)
+        loads = np.array([w[z0:z1].sum() for z0, z1 in b])
+        if nz >= 16 * world:  # fine enough to balance: no slab more than one heavy plane over the mean
+            assert loads.max() - w.sum() / world <= w.max() + 1e-9
+            uniform = np.array([w[z0:z1].sum() for z0, z1 in (slabs.slab_bounds(nz, world, r) for r in range(world))])
+            assert loads.max() <= uniform.max() + 1e-9
+    # uniform weights: equal heights (within one plane)
+    b = slabs.balanced_bounds(np.ones(1000), 8)
+    assert {z1 - z0 for z0, z1 in b} == {125}
+    with pytest.raises(ValueError):
+        slabs.balanced_bounds(np.ones(3), 4)

@@ -20,6 +20,32 @@ def slab_bounds(nz: int, world: int, rank: int) -> tuple[int, int]:
     return z0, z0 + base + (1 if rank < rem else 0)
 
 
+def balanced_bounds(weights, world: int) -> list[tuple[int, int]]:
+    """Contiguous z-slabs of (nearly) equal total WEIGHT instead of equal height: weights[z] is an estimate of the work
+    of vertex plane z (e.g. 1 + c * inside fraction: the measures of a plane cost more where it cuts solids).  Every slab
+    gets at least one plane; returns [(z0, z1)] per rank.  Uniform weights reproduce slab_bounds up to the placement of
+    the remainder.  (Not yet used by bench.py: DESIGN.md section 8 lists it as the next lever for the 8-GPU step.)"""
+    w = np.asarray(weights, np.float64)
+    nz = len(w)
+    if world < 1 or world > nz or (w < 0).any():
+        raise ValueError(f"bad request: {nz} planes, {world} slabs")
+    if not w.sum() > 0:
+        w = np.ones(nz)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        z = int(np.searchsorted(cum, target, side="left"))
+        # the cut nearer to the target of the two around it
+        if z > 0 and abs(cum[z - 1] - target) <= abs(cum[min(z, nz)] - target):
+            z -= 1
+        z = max(z, cuts[-1] + 1)             # at least one plane for the slab below ...
+        z = min(z, nz - (world - r))         # ... and for every slab above
+        cuts.append(z)
+    cuts.append(nz)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def resident_planes(z0: int, z1: int, nz: int) -> tuple[int, int]:
     """Voxel planes a slab needs resident: its own planes plus one halo plane on each interior side
     (the lower one feeds the slab's first corner plane, the upper one the cells that reach up)."""
