@@ -286,6 +286,19 @@ def run_ours(args):
     z0, z1 = slabs.slab_bounds(nz, world, rank)
     lo, hi = slabs.resident_planes(z0, z1, nz)
     planes = make_planes(fam, grid, lo, hi)
+    if world > 1 and args.balance > 0:
+        # EXPERIMENTAL (off by default): slab heights from a per-plane work estimate 1 + c * inside fraction
+        # (slabs.balanced_bounds) instead of equal heights; every rank counts its own planes, the counts are gathered
+        frac = (planes[z0 - lo:z1 - lo] > 0).reshape(z1 - z0, -1).mean(axis=1)
+        per = [None] * world
+        dist.all_gather_object(per, (z0, frac.astype(np.float64)))
+        full = np.zeros(nz)
+        for zz, f in per:
+            full[zz:zz + len(f)] = f
+        z0, z1 = slabs.balanced_bounds(1.0 + args.balance * full, world)[rank]
+        lo, hi = slabs.resident_planes(z0, z1, nz)
+        planes = make_planes(fam, grid, lo, hi)
+        print(f"[rank {rank}] balanced slab [{z0},{z1}) = {z1 - z0} planes", file=sys.stderr)
     ctx = api.Context(local)
     ctx.set_grid(nx, ny, nz, z0, z1)
     # pinned staging of the slab (the e2e leg copies from here every step)
@@ -532,7 +545,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32",
             "data": "synthetic",
-            "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world,
+            "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world, "slab_heights": "equal" if args.balance <= 0 else f"balanced (1 + {args.balance} x inside fraction)",
                        "vertices_per_gpu": nv_local,
                        "exchange": ("none (one slab)" if world == 1 else
                                     "peer memory: detection kernel stores records into every rank over NVLink (vc_peer.cu)"
@@ -598,6 +611,8 @@ def main():
     ap.add_argument("--workload", default=None, help="sphere256 | torus256 | twist512 | assembly1024 ...")
     ap.add_argument("--grid", default=None, help="NX,NY,NZ (assembly family)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--balance", type=float, default=0.0, help="EXPERIMENTAL, N>1: weight c of the per-plane inside fraction in the "
+                    "slab-height estimate 1 + c*fraction (0 = equal heights, the default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (very large grids: the all-planes leg needs "
                     "41 B of pinned host memory per grid vertex)")
     ap.add_argument("--exchange", default="peers", choices=["peers", "nccl"],
