@@ -224,6 +224,9 @@ typedef enum vc_array
 } vc_array;
 /* copy a result array (owned planes) to dst (host or device) */
 int vc_download(vc_ctx* ctx, int which, void* dst);
+/* the same for the planes [za, zb) of the grid only (global z; inside this ctx's owned planes -- for VC_ARR_ID /
+ * VC_ARR_D2X4 also the recomputed halo plane z1 of a slab); EDGE3 / FACE3 arrive as [3][zb-za][y][x] */
+int vc_download_planes(vc_ctx* ctx, int which, int za, int zb, void* dst);
 /* device pointer of a result array (valid until the next stage call / destroy) */
 void* vc_device_ptr(vc_ctx* ctx, int which);
 /* Host-buffer end-to-end step: H2D of the float32 volume, the hot path, D2H of every non-NULL

@@ -71,6 +71,7 @@ def oracle():
         lib.orc_closest_points_f32.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_float, _i32p, C.c_void_p]
         lib.orc_closest_grid.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _i32p, C.c_void_p, C.c_void_p]
+        lib.orc_closest_grid_sample.argtypes = [_f32p, C.c_int64, _i32p, C.c_int64, _i32p, _u32p]
         lib.orc_face_lambda.argtypes = [_f32p, _i32p, C.c_int64, _f32p]
         lib.orc_vertex_radii.argtypes = [_f32p, _f32p, C.c_int64, _i32p, _f32p]
         lib.orc_segment_max.argtypes = [_i32p, _i32p, C.c_int64, _f32p, C.c_void_p, _f32p]
@@ -102,6 +103,7 @@ def ref():
         lib.ref_extract_sites.restype = C.c_int64
         for f in (lib.ref_ann_kd_search, lib.ref_ann_brute_search):
             f.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _i32p, _f64p]
+        lib.ref_ann_kd_grid.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.ref_ann_kd_fr_search.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int64, _f64p, C.c_int,
                                              _i32p, C.c_void_p, C.c_void_p]
         lib.ref_kdtree_closest.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_float, _i32p, _f32p]
@@ -196,10 +198,13 @@ def simple_pairs(edge_ref, edge_face0, face_measure, f_t, vert_ref, vert_edge0, 
 
 def extract_sites(inside: np.ndarray) -> np.ndarray:
     ins = np.ascontiguousarray(inside, np.uint8)
-    n = oracle().orc_extract_sites(ins, *_dims(ins), None, 0)
-    out = np.empty((n, 3), np.float32)
-    oracle().orc_extract_sites(ins, *_dims(ins), out.ctypes.data, n)
-    return out
+    cap = 1 << 22  # one scan when the sites fit the first guess (the scan of a 1024^3 grid takes tens of seconds)
+    out = np.empty((cap, 3), np.float32)
+    n = oracle().orc_extract_sites(ins, *_dims(ins), out.ctypes.data, cap)
+    if n > cap:
+        out = np.empty((n, 3), np.float32)
+        oracle().orc_extract_sites(ins, *_dims(ins), out.ctypes.data, n)
+    return out[:n].copy()
 
 
 def closest_points(sites: np.ndarray, q: np.ndarray):
@@ -231,6 +236,16 @@ def closest_grid(sites_xyz: np.ndarray, nx, ny, nz, z0=0, z1=None, want_d2=False
     oracle().orc_closest_grid(s, len(s), nx, ny, nz, z0, z1, ids, d2x4.ctypes.data,
                               None if d2 is None else d2.ctypes.data)
     return (ids, d2x4, d2) if want_d2 else (ids, d2x4)
+
+
+def closest_grid_sample(sites_xyz, q_xyz):
+    """(lowest id at the minimum distance, 4*d2) at the integer vertices q_xyz [n,3] = (x, y, z): all sites scanned"""
+    s = np.ascontiguousarray(sites_xyz, np.float32).reshape(-1, 3)
+    q = np.ascontiguousarray(q_xyz, np.int32).reshape(-1, 3)
+    ids = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.uint32)
+    oracle().orc_closest_grid_sample(s, len(s), q, len(q), ids, d2)
+    return ids, d2
 
 
 def face_lambda(sites_xyz, site_pairs):
@@ -308,6 +323,46 @@ def ref_ann(sites, q, brute=False):
     fn = ref().ref_ann_brute_search if brute else ref().ref_ann_kd_search
     fn(s, len(s), s.shape[1], q, len(q), idx, d2)
     return idx, d2
+
+
+_ann_grid_shared = None  # (sites, nx, ny, z0, id mapping, d2 mapping): inherited by the forked workers
+
+
+def _ann_grid_worker(span):
+    za, zb = span
+    s, nx, ny, z0, id_buf, d2_buf = _ann_grid_shared
+    n = (zb - za) * ny * nx
+    off = (za - z0) * ny * nx
+    ids = np.frombuffer(id_buf, np.int32, n, off * 4)
+    d2 = np.frombuffer(d2_buf, np.float64, n, off * 8)
+    ref().ref_ann_kd_grid(s, len(s), nx, ny, za, zb, ids.ctypes.data, d2.ctypes.data)
+    return ref().ref_last_seconds()
+
+
+def ref_ann_grid(sites, nx, ny, z0, z1, workers=None):
+    """The real ANNkd_tree::annkSearch(k=1, eps=0) at EVERY grid vertex of the planes [z0, z1): forked
+    processes (ANN's search state is global), each with its own tree per group of planes, results written
+    into shared anonymous mappings.  Returns (ids int32, d2 float64) shaped [z1-z0, ny, nx] and the CPU
+    seconds spent inside the reference (tree builds + queries, summed over the workers)."""
+    global _ann_grid_shared
+    import mmap
+    import multiprocessing as mp
+    s = np.ascontiguousarray(sites, np.float64).reshape(-1, 3)
+    workers = workers or os.cpu_count() or 1
+    n = (z1 - z0) * ny * nx
+    id_buf, d2_buf = mmap.mmap(-1, max(n * 4, 1)), mmap.mmap(-1, max(n * 8, 1))
+    _ann_grid_shared = (s, nx, ny, z0, id_buf, d2_buf)
+    # planes dealt in groups (a few per worker) so that slow, deep regions spread over the workers
+    step = max(1, -(-(z1 - z0) // (workers * 3)))
+    spans = [(za, min(za + step, z1)) for za in range(z0, z1, step)]
+    try:
+        with mp.get_context("fork").Pool(workers) as pool:
+            secs = pool.map(_ann_grid_worker, spans, chunksize=1)
+    finally:
+        _ann_grid_shared = None
+    ids = np.frombuffer(id_buf, np.int32, n).reshape(z1 - z0, ny, nx)
+    d2 = np.frombuffer(d2_buf, np.float64, n).reshape(z1 - z0, ny, nx)
+    return ids, d2, float(sum(secs))
 
 
 def ref_ann_fr(sites, q, sq_rad):

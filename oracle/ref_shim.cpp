@@ -178,6 +178,40 @@ extern "C"
         annClose();
     }
 
+    // a5 at full size: the same ANNkd_tree::annkSearch(k=1, eps=0), one query per grid vertex (x, y, z) of
+    // the planes [z0, z1) -- the dense query set of BASELINE's metric, with no query array to marshal.
+    // id_out / d2_out are [z1-z0][ny][nx], x fastest.  One tree per call (per forked worker: ANN keeps its
+    // search state in globals, 3rdparty/ann/src/kd_search.cpp:78-82).
+    void ref_ann_kd_grid(const double* data, int n, int nx, int ny, int z0, int z1, int32_t* id_out, double* d2_out)
+    {
+        ANNpointArray pa = annAllocPts(n, 3);
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d)
+                pa[i][d] = data[(size_t)i * 3 + d];
+        {
+            Stopwatch sw;
+            ANNkd_tree tree(pa, n, 3);
+            ANNpoint qq = annAllocPt(3);
+            size_t o = 0;
+            for (int z = z0; z < z1; ++z)
+                for (int y = 0; y < ny; ++y)
+                    for (int x = 0; x < nx; ++x, ++o)
+                    {
+                        qq[0] = x;
+                        qq[1] = y;
+                        qq[2] = z;
+                        ANNidx id;
+                        ANNdist dd;
+                        tree.annkSearch(qq, 1, &id, &dd, 0.0);
+                        id_out[o] = id;
+                        d2_out[o] = dd;
+                    }
+            annDeallocPt(qq);
+        }
+        annDeallocPts(pa);
+        annClose();
+    }
+
     // f-2: trimesh::KDtree::closest_to_pt as estimateRadiiField calls it (src/exporters.cpp:626-637):
     // idx = index of the returned point (-1 when NULL), d = trimesh::dist(point(closest), v)
     void ref_kdtree_closest(const float* pts, int64_t n, const float* q, int64_t nq, float maxdist2, int32_t* idx,

@@ -106,6 +106,117 @@ extern "C"
     }
 
 
+    // The round-2 data flow of the transform (vc_edt.cu): compact site-bearing columns, live rows, pruned
+    // envelopes.  stats (nullable, 8 x int64): [0] lines X, [1] candidates X, [2] pops X, [3] max depth X,
+    // [4..7] the same for pass Y; depth_hist (nullable, 2 x 64 x int64): histogram of the per-line max depth, bin = min(depth, 63)
+    void hh_closest_grid2(const int32_t* corners, int64_t ns, int nx, int ny, int nz, int z0, int z1, int32_t* id_out,
+                          uint32_t* d2x4_out, int64_t* stats, int64_t* depth_hist)
+    {
+        const int CX = nx + 1, CY = ny + 1;
+        const int nzs = z1 - z0;
+        std::vector<double> rcp(2050, 0.0);
+        for (int w = 1; w < 2050; ++w)
+            rcp[w] = 1.0 / (8.0 * w);
+        // z-line lists per column, then the compact list of columns that hold sites, row by row (cy major, cx ascending)
+        std::vector<std::vector<vc_u64>> lines((size_t)CX * CY);
+        for (int64_t s = 0; s < ns; ++s)
+            lines[(size_t)corners[3 * s + 1] * CX + corners[3 * s]].push_back(((vc_u64)corners[3 * s + 2] << 32) | (uint32_t)s);
+        std::vector<int> rowptr(CY + 1, 0), colx, colline, liverow;
+        for (int cy = 0; cy < CY; ++cy)
+        {
+            for (int cx = 0; cx < CX; ++cx)
+                if (!lines[(size_t)cy * CX + cx].empty())
+                {
+                    std::sort(lines[(size_t)cy * CX + cx].begin(), lines[(size_t)cy * CX + cx].end());
+                    colx.push_back(cx);
+                    colline.push_back(cy * CX + cx);
+                }
+            rowptr[cy + 1] = (int)colx.size();
+            if (rowptr[cy + 1] > rowptr[cy])
+                liverow.push_back(cy);
+        }
+        const int ncol = (int)colx.size(), nlive = (int)liverow.size();
+        // pass Z: G1c[col][vz]
+        std::vector<vc_u64> G1((size_t)ncol * nzs), G2((size_t)nzs * std::max(nlive, 1) * nx);
+        for (int c = 0; c < ncol; ++c)
+        {
+            const auto& l = lines[colline[c]];
+            int last = (int)l.size(), lo = -1;
+            for (int vz = z0; vz < z1; ++vz)
+            {
+                while (lo + 1 < last && (int)(l[lo + 1] >> 32) <= vz)
+                    ++lo;
+                G1[(size_t)c * nzs + (vz - z0)] = vc_nearest_on_zline(l.data(), 0, last, lo, vz);
+            }
+        }
+        std::vector<vc_ent> stkv(std::max(CX, CY) + 2);
+        int64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // pass X: lines (live row, vz) over the row's compact columns -> G2[vz][live row][vx]
+        for (int r = 0; r < nlive; ++r)
+            for (int vz = 0; vz < nzs; ++vz)
+            {
+                const int cy = liverow[r], c0 = rowptr[cy], nc = rowptr[cy + 1] - c0;
+                vc_u64* row = &G2[((size_t)vz * nlive + r) * nx];
+                vc_pstack_array stk{stkv.data()};
+                int np = vc_envelope_pruned(
+                    nc, [&](int k, vc_u64& H, int& p) { H = G1[(size_t)(c0 + k) * nzs + vz]; p = colx[c0 + k]; }, nx, stk,
+                    [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; }, rcp.data());
+                st[0]++, st[1] += nc, st[2] += np, st[3] = std::max<int64_t>(st[3], stk.maxdepth + 1);
+                if (depth_hist)
+                    depth_hist[std::min(stk.maxdepth + 1, 63)]++;
+            }
+        // pass Y: lines (vz, vx) over the live rows -> out[vz][vy][vx]
+        for (int vz = 0; vz < nzs; ++vz)
+            for (int vx = 0; vx < nx; ++vx)
+            {
+                vc_pstack_array stk{stkv.data()};
+                int np = vc_envelope_pruned(
+                    nlive, [&](int k, vc_u64& H, int& p) { H = G2[((size_t)vz * nlive + k) * nx + vx]; p = liverow[k]; }, ny, stk,
+                    [&](int t, uint32_t V, uint32_t id)
+                    {
+                        size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
+                        id_out[o] = (int32_t)id;
+                        d2x4_out[o] = V;
+                    },
+                    rcp.data());
+                st[4]++, st[5] += nlive, st[6] += np, st[7] = std::max<int64_t>(st[7], stk.maxdepth + 1);
+                if (depth_hist)
+                    depth_hist[64 + std::min(stk.maxdepth + 1, 63)]++;
+            }
+        if (stats)
+            memcpy(stats, st, sizeof st);
+    }
+
+    // vc_sep against plain integer floor division: returns the number of mismatches over all divisors w in [1, 2048]
+    // and the numerators around every multiple of 8w plus the extremes
+    int64_t hh_sep_sweep(void)
+    {
+        std::vector<double> rcp(2050, 0.0);
+        for (int w = 1; w < 2050; ++w)
+            rcp[w] = 1.0 / (8.0 * w);
+        int64_t bad = 0;
+        auto fl = [](long long a, long long b) { long long q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+        for (int w = 1; w <= 2048; ++w)
+        {
+            const long long d = 8LL * w;
+            auto check = [&](long long N)
+            { // N = dg + c - 1 + 4w  ->  dg = N - c + 1 - 4w with c = 0
+                if (N < -(1LL << 28) || N > (1LL << 28))
+                    return;
+                int got = vc_sep((int)(N + 1 - 4 * w), 0, w, rcp.data());
+                if (got != (int)fl(N, d))
+                    ++bad;
+            };
+            for (long long k = -(1LL << 27) / d - 1; k <= (1LL << 27) / d + 1; k += std::max<long long>(1, ((1LL << 27) / d) / 3000))
+                for (int e = -2; e <= 2; ++e)
+                    check(k * d + e);
+            for (long long N = -40000; N <= 40000; ++N)
+                check(N);
+            check((1LL << 28) - 1), check(-(1LL << 28) + 1);
+        }
+        return bad;
+    }
+
     // one line of the transform on caller data (robustness tests with 2048-scale coordinates)
     void hh_envelope(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
     {

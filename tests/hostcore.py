@@ -47,6 +47,23 @@ def closest_grid(sites_xyz, nx, ny, nz, z0=0, z1=None):
     return ids, d2
 
 
+def closest_grid2(sites_xyz, nx, ny, nz, z0=0, z1=None, want_stats=False):
+    """round-2 data flow: compact columns, live rows, pruned (Meijster-style) envelopes"""
+    z1 = nz if z1 is None else z1
+    c = np.ascontiguousarray(np.round(np.asarray(sites_xyz) + 0.5).astype(np.int32))
+    ids = np.empty((z1 - z0, ny, nx), np.int32)
+    d2 = np.empty((z1 - z0, ny, nx), np.uint32)
+    stats = np.zeros(8, np.int64)
+    hist = np.zeros((2, 64), np.int64)
+    lib().hh_closest_grid2(_p(c), C.c_int64(len(c)), nx, ny, nz, z0, z1, _p(ids), _p(d2), _p(stats), _p(hist))
+    return (ids, d2, stats, hist) if want_stats else (ids, d2)
+
+
+def sep_sweep():
+    lib().hh_sep_sweep.restype = C.c_int64
+    return int(lib().hh_sep_sweep())
+
+
 def envelope(H, ntgt):
     H = np.ascontiguousarray(H, np.uint64)
     out = np.empty(ntgt, np.uint64)

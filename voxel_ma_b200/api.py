@@ -26,7 +26,7 @@ SYMBOLS = [
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
     "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_closest_points_f32", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
-    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
+    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_download_planes", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
     "vc_run_dense_host_compact", "vc_run_dense_host_compact_i8", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
@@ -105,6 +105,7 @@ def load_library(path: str | None = None):
     lib.vc_closest_and_measures.argtypes = [vp]
     lib.vc_set_pipeline.argtypes = [vp, i32, i32]
     lib.vc_download.argtypes = [vp, i32, vp]
+    lib.vc_download_planes.argtypes = [vp, i32, i32, i32, vp]
     lib.vc_device_ptr.argtypes = [vp, i32]
     lib.vc_device_ptr.restype = vp
     lib.vc_run_dense_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
@@ -403,6 +404,18 @@ class Context:
         }[which]
         out = np.empty(shape, dt)
         self._ck(self.lib.vc_download(self.h, which, _ptr(out)))
+        return out
+
+    def download_planes(self, which, za, zb) -> np.ndarray:
+        """planes [za, zb) (global z) of a result array; ids / 4d2 may include the halo plane z1 of a slab"""
+        s = (zb - za,) + self.slab_shape[1:]
+        shape, dt = {
+            ARR_INSIDE: (s, np.uint8), ARR_ID: (s, np.int32), ARR_D2X4: (s, np.uint32),
+            ARR_EDGE3: ((3,) + s, np.float32), ARR_FACE3: ((3,) + s, np.float32),
+            ARR_CUBE: (s, np.float32), ARR_RADIUS: (s, np.float32),
+        }[which]
+        out = np.empty(shape, dt)
+        self._ck(self.lib.vc_download_planes(self.h, which, za, zb, _ptr(out)))
         return out
 
     def device_ptr(self, which) -> int:

@@ -631,6 +631,31 @@ extern "C"
         return VC_OK;
     }
 
+    int vc_download_planes(vc_ctx* c, int which, int za, int zb, void* dst)
+    {
+        if (!c || !dst)
+            return VC_ERR_INVALID;
+        VC_CUDA(c, cudaSetDevice(c->device));
+        void* p = nullptr;
+        size_t bytes = 0;
+        VC_TRY(result_array(c, which, &p, &bytes));
+        // the closest-site planes also hold the recomputed halo plane z1 of a slab (planes [z0, zc))
+        const int zend = (which == VC_ARR_ID || which == VC_ARR_D2X4) ? c->zc : c->z1;
+        if (za < c->z0 || zb > zend || za > zb)
+            return vc_fail(c, VC_ERR_INVALID, "vc_download_planes: plane range outside this ctx's planes");
+        const size_t plane = (size_t)c->nx * c->ny;
+        const int ncomp = (which == VC_ARR_EDGE3 || which == VC_ARR_FACE3) ? 3 : 1;
+        const size_t esz = which == VC_ARR_INSIDE ? 1 : 4;
+        const size_t row = plane * (size_t)(zb - za) * esz, comp_pitch = plane * (size_t)(c->z1 - c->z0) * esz;
+        const char* src = (const char*)p + plane * (size_t)(za - c->z0) * esz;
+        if (row && ncomp == 1)
+            VC_CUDA(c, cudaMemcpyAsync(dst, src, row, cudaMemcpyDefault, c->stream));
+        else if (row)
+            VC_CUDA(c, cudaMemcpy2DAsync(dst, row, src, comp_pitch, row, ncomp, cudaMemcpyDefault, c->stream));
+        VC_CUDA(c, cudaStreamSynchronize(c->stream));
+        return VC_OK;
+    }
+
     void* vc_device_ptr(vc_ctx* c, int which)
     {
         if (!c)

@@ -237,6 +237,109 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
     }
 }
 
+// ---- pruned envelope (round 2) ---------------------------------------------------------------------
+// The same 1-D pass as a Meijster-style scan on the TOTAL order of the words (4d^2, id): a candidate v "beats" u
+// at target t iff (V_v(t), id_v) < (V_u(t), id_u) lexicographically.  For u left of v that holds exactly for
+// t >= sep(u, v): V_v(t) - V_u(t) = (g_v - g_u) - 4 (v - u) x with x = 2t + 1 falls monotonically, so with
+// c = (id_v < id_u ? 0 : 1) the condition is 4 w x >= dg + c  (w = v - u, dg = g_v - g_u), i.e.
+//     sep(u, v) = floor((dg + c - 1 + 4w) / (8w)).
+// The stack keeps only candidates that are the strict minimum at >= 1 integer target of [0, ntgt): each entry
+// carries the first target `start` at which it beats the entry below it, starts increase strictly up the stack,
+// a new candidate pops the top while it beats it at the top's own start and is dropped when its start would lie
+// beyond the last target.  The backward scan is then a walk: the top is the winner until t == start, no compares.
+// Distance ties never need a second look (the id is part of the order), and the stack depth is bounded by the
+// number of distinct winners of the line instead of the number of parabolas touching the real-valued envelope.
+//
+// The one division is done in double: |N| < 2^28, divisor 8w <= 2^14; the true quotient of (N + 0.5) / (8w) is
+// at least 2^-15 away from every integer and the product with the rounded reciprocal is off by < 2^-24, so the
+// floor is exact (tests/test_host_core.py sweeps every divisor).  rcp8w[w] = 1.0 / (8 w), w in [1, 2048].
+VC_HD int vc_sep(int dg, int c, int w, const double* __restrict__ rcp8w)
+{
+    const int N = dg + c - 1 + 4 * w;
+#if defined(__CUDA_ARCH__)
+    return __double2int_rd(((double)N + 0.5) * rcp8w[w]);
+#else
+    double qd = ((double)N + 0.5) * rcp8w[w];
+    int q = (int)qd;
+    return (double)q > qd ? q - 1 : q; // floor
+#endif
+}
+
+struct vc_ent
+{
+    int g;       // D + 4 p^2
+    uint32_t id; // site id
+    int p;       // position on the candidate axis
+    int start;   // first target at which this entry beats the one below it (0 for the bottom)
+};
+
+// plain-array stack (CPU harness): depth d at a[d]
+struct vc_pstack_array
+{
+    vc_ent* a;
+    int maxdepth = 0;
+    VC_HD void store(int d, const vc_ent& e)
+    {
+        a[d] = e;
+        if (d + 1 > maxdepth)
+            maxdepth = d + 1;
+    }
+    VC_HD vc_ent load(int d) { return a[d]; }
+};
+
+// cand(k, H, p): k-th LIVE candidate of the line (ascending position p, H finite); emit(t, V, id) for t = ntgt-1 .. 0
+// (all-ones when the line has no candidate).  Returns the number of pops of the forward scan (statistics).
+template <class Cand, class Stack, class Emit>
+VC_HD int vc_envelope_pruned(int ncand, Cand cand, int ntgt, Stack& stk, Emit emit, const double* __restrict__ rcp8w)
+{
+    int q = -1, npop = 0; // q = depth of the top, which lives in `top`; depths 0 .. q-1 are in stk
+    vc_ent top = {0, 0u, 0, 0};
+    for (int k = 0; k < ncand; ++k)
+    {
+        vc_u64 H;
+        int j;
+        cand(k, H, j);
+        const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
+        const uint32_t id = (uint32_t)H;
+        while (q >= 0)
+        { // new - top at the top's own start; the top survives iff it still wins there
+            const int diff = (g - top.g) - 4 * (j - top.p) * (2 * top.start + 1);
+            if (diff > 0 || (diff == 0 && id >= top.id))
+                break;
+            --q;
+            ++npop;
+            if (q >= 0)
+                top = stk.load(q);
+        }
+        int s = 0;
+        if (q >= 0)
+        {
+            s = vc_sep(g - top.g, id < top.id ? 0 : 1, j - top.p, rcp8w);
+            if (s >= ntgt)
+                continue; // never the winner inside the line
+            stk.store(q, top);
+        }
+        top.g = g;
+        top.id = id;
+        top.p = j;
+        top.start = s;
+        ++q;
+    }
+    int x = 2 * (ntgt - 1) + 1;
+    for (int t = ntgt - 1; t >= 0; --t, x -= 2)
+    {
+        if (q < 0)
+        {
+            emit(t, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            continue;
+        }
+        emit(t, (uint32_t)(top.g + x * (x - 4 * top.p)), top.id);
+        if (t == top.start && t > 0)
+            top = stk.load(--q);
+    }
+    return npop;
+}
+
 // First pass (along z) straight from a line's sorted site list: entries e[i] = (cz << 32) | id,
 // ascending cz.  `lo` = index of the last entry with cz <= vz (or first-1), maintained by the caller.
 VC_HD vc_u64 vc_nearest_on_zline(const vc_u64* __restrict__ e, int first, int last, int lo, int vz)
