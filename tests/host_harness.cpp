@@ -158,10 +158,9 @@ extern "C"
                 const int cy = liverow[r], c0 = rowptr[cy], nc = rowptr[cy + 1] - c0;
                 vc_u64* row = &G2[((size_t)vz * nlive + r) * nx];
                 vc_pstack_array stk{stkv.data()};
-                int np = vc_envelope_pruned(
-                    nc, [&](int k, vc_u64& H, int& p) { H = G1[(size_t)(c0 + k) * nzs + vz]; p = colx[c0 + k]; }, nx, stk,
-                    [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; }, rcp.data());
-                st[0]++, st[1] += nc, st[2] += np, st[3] = std::max<int64_t>(st[3], stk.maxdepth + 1);
+                vc_envelope_pruned(&G1[(size_t)c0 * nzs + vz], (long)nzs, &colx[c0], nc, nx, stk,
+                                   [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; }, rcp.data());
+                st[0]++, st[1] += nc, st[2] += stk.npop, st[3] = std::max<int64_t>(st[3], stk.maxdepth + 1);
                 if (depth_hist)
                     depth_hist[std::min(stk.maxdepth + 1, 63)]++;
             }
@@ -170,21 +169,38 @@ extern "C"
             for (int vx = 0; vx < nx; ++vx)
             {
                 vc_pstack_array stk{stkv.data()};
-                int np = vc_envelope_pruned(
-                    nlive, [&](int k, vc_u64& H, int& p) { H = G2[((size_t)vz * nlive + k) * nx + vx]; p = liverow[k]; }, ny, stk,
-                    [&](int t, uint32_t V, uint32_t id)
-                    {
-                        size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
-                        id_out[o] = (int32_t)id;
-                        d2x4_out[o] = V;
-                    },
-                    rcp.data());
-                st[4]++, st[5] += nlive, st[6] += np, st[7] = std::max<int64_t>(st[7], stk.maxdepth + 1);
+                vc_envelope_pruned(&G2[(size_t)vz * nlive * nx + vx], (long)nx, liverow.data(), nlive, ny, stk,
+                                   [&](int t, uint32_t V, uint32_t id)
+                                   {
+                                       size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
+                                       id_out[o] = (int32_t)id;
+                                       d2x4_out[o] = V;
+                                   },
+                                   rcp.data());
+                st[4]++, st[5] += nlive, st[6] += stk.npop, st[7] = std::max<int64_t>(st[7], stk.maxdepth + 1);
                 if (depth_hist)
                     depth_hist[64 + std::min(stk.maxdepth + 1, 63)]++;
             }
         if (stats)
             memcpy(stats, st, sizeof st);
+    }
+
+    // one line through the pruned scan: the finite candidates of `in` are compacted (position list), as the kernels
+    // only ever see live candidates
+    void hh_envelope_pruned(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
+    {
+        std::vector<double> rcp(2050, 0.0);
+        for (int w = 1; w < 2050; ++w)
+            rcp[w] = 1.0 / (8.0 * w);
+        std::vector<vc_u64> h;
+        std::vector<int> pos;
+        for (int j = 0; j < ncand; ++j)
+            if (in[j] != VC_INF)
+                h.push_back(in[j]), pos.push_back(j);
+        std::vector<vc_ent> stkv(ncand + 2);
+        vc_pstack_array stk{stkv.data()};
+        vc_envelope_pruned(h.data(), 1L, pos.data(), (int)h.size(), ntgt, stk,
+                           [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; }, rcp.data());
     }
 
     // vc_sep against plain integer floor division: returns the number of mismatches over all divisors w in [1, 2048]

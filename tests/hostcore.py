@@ -71,6 +71,14 @@ def envelope(H, ntgt):
     return out
 
 
+def envelope_pruned(H, ntgt):
+    """the same line through the round-2 scan (vc_envelope_pruned) over the compacted live candidates"""
+    H = np.ascontiguousarray(H, np.uint64)
+    out = np.empty(ntgt, np.uint64)
+    lib().hh_envelope_pruned(_p(H), len(H), ntgt, _p(out))
+    return out
+
+
 def envelope_masked(H, ntgt):
     """same line through the candidate-bitmap path of pass X (dead candidates hold garbage)"""
     H = np.ascontiguousarray(H, np.uint64)

@@ -53,11 +53,16 @@ def test_envelope_line_random(n, dmax, density):
         H[rng.random(n) > density] = np.uint64(0xFFFFFFFFFFFFFFFF)
         out = hc.envelope(H, n - 1)
         assert np.array_equal(out, _brute_line(H, n - 1))
+        assert np.array_equal(hc.envelope_pruned(H, n - 1), out)
         # pass X's form: a bitmap says which candidates exist, the others are never read
         assert np.array_equal(hc.envelope_masked(H, n - 1), out)
+        # the round-2 scan (the one the kernels run): integer-pruned stack over the live candidates
+        assert np.array_equal(hc.envelope_pruned(H, n - 1), out)
+        assert np.array_equal(hc.envelope_pruned(H, max(n // 3, 1)), _brute_line(H, max(n // 3, 1)))  # targets end early
     empty = np.full(n, 0xFFFFFFFFFFFFFFFF, np.uint64)
     assert (hc.envelope(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
     assert (hc.envelope_masked(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    assert (hc.envelope_pruned(empty, n - 1) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
 
 
 @pytest.mark.parametrize("n,levels", [(33, 2), (257, 3), (1025, 2), (2049, 4)])
@@ -76,3 +81,25 @@ def test_envelope_line_touching_parabolas(n, levels):
         H[rng.random(n) > 0.8] = np.uint64(0xFFFFFFFFFFFFFFFF)
         out = hc.envelope(H, n - 1)
         assert np.array_equal(out, _brute_line(H, n - 1))
+        assert np.array_equal(hc.envelope_pruned(H, n - 1), out)
+
+
+def test_sep_division_is_exact():
+    """vc_sep's double-precision floor division against integer arithmetic: every divisor 8w, w in [1, 2048]"""
+    assert hc.sep_sweep() == 0
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_round2_data_flow_is_exact(name):
+    """compact columns -> pass Z -> pass X over the row's columns -> pass Y over the live rows (vc_edt.cu's data flow)"""
+    vol = CASES[name]
+    nz, ny, nx = vol.shape
+    sites = ob.extract_sites(ob.classify_grid(vol))
+    if len(sites) == 0:
+        pytest.skip("no boundary")
+    o_ids, o_d2 = ob.closest_grid(sites, nx, ny, nz)
+    ids, d2 = hc.closest_grid2(sites, nx, ny, nz)
+    assert np.array_equal(d2, o_d2) and np.array_equal(ids, o_ids)
+    if nz > 6:
+        ids2, d22 = hc.closest_grid2(sites, nx, ny, nz, 2, nz - 3)
+        assert np.array_equal(ids2, o_ids[2:nz - 3]) and np.array_equal(d22, o_d2[2:nz - 3])

@@ -265,7 +265,11 @@ VC_HD int vc_sep(int dg, int c, int w, const double* __restrict__ rcp8w)
 #endif
 }
 
-struct vc_ent
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#endif
+    vc_ent
 {
     int g;       // D + 4 p^2
     uint32_t id; // site id
@@ -273,71 +277,144 @@ struct vc_ent
     int start;   // first target at which this entry beats the one below it (0 for the bottom)
 };
 
-// plain-array stack (CPU harness): depth d at a[d]
+// Storage of the stack entries below the top (which lives in registers), depths d = 0 .. q-1.  The scan is
+// written against this interface so that the device keeps the upper entries in a shared-memory ring that spills
+// to global memory (vc_edt.cu: StackRing) while the CPU harness uses a plain array:
+//   store(d, e)      entry at depth d := e          (forward scan, d = current depth of the top)
+//   load(d)          entry at depth d               (forward scan pops)
+//   begin_drain(d)   the backward scan starts: depths d, d-1, ... 0 will be read in exactly that order
+//   drain(d)         entry at depth d, in drain order
 struct vc_pstack_array
 {
     vc_ent* a;
-    int maxdepth = 0;
+    int maxdepth = 0, npop = 0;
     VC_HD void store(int d, const vc_ent& e)
     {
         a[d] = e;
         if (d + 1 > maxdepth)
             maxdepth = d + 1;
     }
-    VC_HD vc_ent load(int d) { return a[d]; }
+    VC_HD vc_ent load(int d)
+    {
+        ++npop;
+        return a[d];
+    }
+    VC_HD void begin_drain(int) {}
+    VC_HD vc_ent drain(int d) { return a[d]; }
 };
 
-// cand(k, H, p): k-th LIVE candidate of the line (ascending position p, H finite); emit(t, V, id) for t = ntgt-1 .. 0
-// (all-ones when the line has no candidate).  Returns the number of pops of the forward scan (statistics).
-template <class Cand, class Stack, class Emit>
-VC_HD int vc_envelope_pruned(int ncand, Cand cand, int ntgt, Stack& stk, Emit emit, const double* __restrict__ rcp8w)
+// One line.  src + k * stride = word (4 D << 32 | id) of the k-th LIVE candidate (all finite), pos[k] = its position
+// on the candidate axis, ascending -- on the device pos is the same array for every lane of a warp, so the scan's
+// control flow only diverges in the pops.  The fetch is software-pipelined VC_EPF candidates ahead.
+// emit(t, V, id) is called for t = ntgt-1 .. 0 (all-ones when the line has no candidate).
+#ifndef VC_EPF
+#define VC_EPF 4
+#endif
+#if defined(__CUDA_ARCH__)
+#define VC_LOAD_POS(p) __ldg(p)
+#else
+#define VC_LOAD_POS(p) (*(p))
+#endif
+template <class Stack, class Emit>
+VC_HD void vc_envelope_pruned(const vc_u64* __restrict__ src, long stride, const int* __restrict__ pos, int ncand, int ntgt,
+                              Stack& stk, Emit emit, const double* __restrict__ rcp8w)
 {
-    int q = -1, npop = 0; // q = depth of the top, which lives in `top`; depths 0 .. q-1 are in stk
-    vc_ent top = {0, 0u, 0, 0};
-    for (int k = 0; k < ncand; ++k)
+    int q = -1; // depth of the top (registers); depths 0 .. q-1 are in stk
+    int gt = 0, pt = 0, st = 0, at = 0; // at = 4 (2 st + 1)
+    uint32_t idt = 0;
+    vc_u64 hb[VC_EPF];
+    int pb[VC_EPF];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < VC_EPF; ++i)
+        if (i < ncand)
+        {
+            hb[i] = VC_LOAD_STREAM(src + (long)i * stride);
+            pb[i] = VC_LOAD_POS(pos + i);
+        }
+    for (int k0 = 0; k0 < ncand; k0 += VC_EPF)
     {
-        vc_u64 H;
-        int j;
-        cand(k, H, j);
-        const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
-        const uint32_t id = (uint32_t)H;
-        while (q >= 0)
-        { // new - top at the top's own start; the top survives iff it still wins there
-            const int diff = (g - top.g) - 4 * (j - top.p) * (2 * top.start + 1);
-            if (diff > 0 || (diff == 0 && id >= top.id))
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < VC_EPF; ++i)
+        {
+            const int k = k0 + i;
+            if (k >= ncand)
                 break;
-            --q;
-            ++npop;
+            const vc_u64 H = hb[i];
+            const int j = pb[i];
+            if (k + VC_EPF < ncand)
+            {
+                hb[i] = VC_LOAD_STREAM(src + (long)(k + VC_EPF) * stride);
+                pb[i] = VC_LOAD_POS(pos + k + VC_EPF);
+            }
+            const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
+            const uint32_t id = (uint32_t)H;
+            while (q >= 0)
+            { // new - top at the top's own start; the top survives iff it still wins there
+                const int diff = (g - gt) - (j - pt) * at;
+                if (diff > 0 || (diff == 0 && id >= idt))
+                    break;
+                --q;
+                if (q >= 0)
+                {
+                    const vc_ent e = stk.load(q);
+                    gt = e.g;
+                    idt = e.id;
+                    pt = e.p;
+                    st = e.start;
+                    at = 8 * st + 4;
+                }
+            }
+            int s = 0;
             if (q >= 0)
-                top = stk.load(q);
+            {
+                s = vc_sep(g - gt, id < idt ? 0 : 1, j - pt, rcp8w);
+                if (s >= ntgt)
+                    continue; // never the winner inside the line
+                vc_ent e;
+                e.g = gt;
+                e.id = idt;
+                e.p = pt;
+                e.start = st;
+                stk.store(q, e);
+            }
+            gt = g;
+            idt = id;
+            pt = j;
+            st = s;
+            at = 8 * s + 4;
+            ++q;
         }
-        int s = 0;
-        if (q >= 0)
-        {
-            s = vc_sep(g - top.g, id < top.id ? 0 : 1, j - top.p, rcp8w);
-            if (s >= ntgt)
-                continue; // never the winner inside the line
-            stk.store(q, top);
-        }
-        top.g = g;
-        top.id = id;
-        top.p = j;
-        top.start = s;
-        ++q;
     }
+    // Backward scan: the top is the winner until t == its start.  V(t) = g + x (x - 4p) with x = 2t + 1;
+    // V(t-1) = V(t) - m with m = 4 (x - 2p - 1), and m itself falls by 8 per step.
+    stk.begin_drain(q - 1);
     int x = 2 * (ntgt - 1) + 1;
-    for (int t = ntgt - 1; t >= 0; --t, x -= 2)
+    uint32_t V = (uint32_t)(gt + x * (x - 4 * pt));
+    int m = 4 * (x - 2 * pt - 1);
+    for (int t = ntgt - 1; t >= 0; --t)
     {
-        if (q < 0)
+        emit(t, q < 0 ? 0xFFFFFFFFu : V, q < 0 ? 0xFFFFFFFFu : idt);
+        x -= 2;
+        if (t == st && t > 0 && q > 0)
         {
-            emit(t, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            continue;
+            const vc_ent e = stk.drain(--q);
+            gt = e.g;
+            idt = e.id;
+            pt = e.p;
+            st = e.start;
+            V = (uint32_t)(gt + x * (x - 4 * pt));
+            m = 4 * (x - 2 * pt - 1);
         }
-        emit(t, (uint32_t)(top.g + x * (x - 4 * top.p)), top.id);
-        if (t == top.start && t > 0)
-            top = stk.load(--q);
+        else
+        {
+            V -= (uint32_t)m;
+            m -= 8;
+        }
     }
-    return npop;
 }
 
 // First pass (along z) straight from a line's sorted site list: entries e[i] = (cz << 32) | id,

@@ -4,106 +4,183 @@
 // (3rdparty/ann/src/kd_search.cpp:88-216) with ANNbruteForce's tie rule
 // (3rdparty/ann/src/brute.cpp:56-82): winner = lexicographic min of (d^2, site id).
 //
-// Sites lie on the corner lattice, so the minimum separates exactly over the axes (vc_core.h):
-//   pass Z  (sparse -> dense)  G1[vz][cx][cy] = min over the sites of z-line (cx,cy)
-//   pass X  G2[vz][cy][vx]     = min_cx  G1[vz][cx][cy] + (2(vx-cx)+1)^2      lanes along cy
-//   pass Y  out[vz][vy][vx]    = min_cy  G2[vz][cy][vx] + (2(vy-cy)+1)^2      lanes along vx
-// Each 1-D pass is a lower envelope of equal-width parabolas (Meijster-style two scans) carried out
-// on 64-bit (4d^2<<32 | id) words, so ties in distance resolve to the lowest id inside the pass.
-// One thread owns one line; the 32 lanes of a warp own 32 lines adjacent in the fastest-varying
-// index of the layout, so every global access of the scans is a coalesced 256-byte row.
-// The slab is independent per vz plane after pass Z: no exchange between GPUs (halo planes are
-// recomputed).
+// Sites lie on the corner lattice, so the minimum separates exactly over the axes (vc_core.h).  Round-2
+// data flow -- every pass walks only candidates that exist, and the candidates of a warp are UNIFORM:
+//   columns   the (cx,cy) z-lines that hold sites, numbered row by row (cy major, cx ascending): `col_x`,
+//             `col_line`, `row_ptr[cy]`; the rows that hold any: `live_row` (k_col_rows / k_col_fill)
+//   pass Z    G1c[col][vz]       = min over the sites of the column              lanes along vz
+//   pass X    G2c[vz][row][vx]   = min over the row's columns  G1c + (2(vx-cx)+1)^2
+//             line = (live row, vz); the 32 lanes of a warp are 32 consecutive vz of ONE row, so they all
+//             walk the same column list: no dead candidates, no per-lane bitmap, coalesced G1c reads
+//   pass Y    out[vz][vy][vx]    = min over the live rows  G2c + (2(vy-cy)+1)^2
+//             line = (vz, vx), lanes along vx; the candidate list (the live rows) is the same for every line
+// Each 1-D pass is vc_envelope_pruned's scan (Meijster-style on the total order (4d^2, id): the stack keeps
+// only candidates that win at >= 1 integer target and the first target each wins at), written out below
+// with the device stack in a shared-memory ring that spills to a per-line array (StackRing below).
+// The planes of a slab are independent after pass Z: no exchange between GPUs (halo planes are recomputed,
+// SURVEY section 8e).
 #include "vc_internal.h"
 
-// ---- pass Z -----------------------------------------------------------------------------------
-// One thread walks one z-line's site list over a chunk of PZ_CHUNK planes (blockIdx.y = chunk), so
-// the grid has (lines x chunks) threads instead of one per line; lanes are adjacent lines (cy
-// fastest), every store is a coalesced 256-byte row of G1.
-#define PZ_CHUNK 32
-__global__ void __launch_bounds__(256)
-    k_pass_z(const int* __restrict__ line_ptr, const u64* __restrict__ ent, u64* __restrict__ G1, int nlines, int z0,
-             int zc)
+// ---- compact columns ---------------------------------------------------------------------------------
+// meta[0] = number of columns with sites, meta[1] = number of live rows
+__global__ void __launch_bounds__(1024)
+    k_col_rows(const u32* __restrict__ colmask, int CY, int nw, int* __restrict__ row_ptr, int* __restrict__ live_row,
+               int* __restrict__ meta)
 {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlines)
-        return;
-    const int zb = z0 + blockIdx.y * PZ_CHUNK; // G1 points at plane z0 of this launch
-    const int ze = min(zb + PZ_CHUNK, zc);
-    const int first = line_ptr[l], last = line_ptr[l + 1];
-    const size_t plane = (size_t)nlines;
-    u64* out = G1 + l + plane * (size_t)(zb - z0);
-    if (first == last)
-        return; // a column without sites: pass X knows from the column mask and never reads these entries
-    int nxt = first; // index of the first entry with cz > vz
-    u64 below = VC_INF, above = ent[first];
-    for (int vz = zb; vz < ze; ++vz, out += plane)
+    __shared__ int cnt[2052], liv[2052];
+    for (int cy = threadIdx.x; cy < CY; cy += blockDim.x)
     {
-        while (nxt < last && (int)(above >> 32) <= vz)
+        int s = 0;
+        for (int w = 0; w < nw; ++w)
+            s += __popc(colmask[(size_t)cy * nw + w]);
+        cnt[cy] = s;
+        liv[cy] = s > 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    { // one warp scans the <= 2049 rows, 32 at a time
+        int carry = 0, lcarry = 0;
+        for (int b = 0; b < CY; b += 32)
         {
-            below = above;
-            ++nxt;
-            above = nxt < last ? ent[nxt] : (u64)VC_INF;
+            const int cy = b + threadIdx.x;
+            const int v = cy < CY ? cnt[cy] : 0, l = cy < CY ? liv[cy] : 0;
+            int inc = v, linc = l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o), u = __shfl_up_sync(0xffffffffu, linc, o);
+                if ((int)threadIdx.x >= o)
+                {
+                    inc += t;
+                    linc += u;
+                }
+            }
+            if (cy < CY)
+            {
+                row_ptr[cy] = carry + inc - v;
+                if (l)
+                    live_row[lcarry + linc - 1] = cy;
+            }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+            lcarry += __shfl_sync(0xffffffffu, linc, 31);
         }
-        u64 H = VC_INF;
-        if (below != VC_INF)
+        if (threadIdx.x == 0)
         {
-            int d = 2 * (vz - (int)(below >> 32)) + 1;
-            H = ((u64)(u32)(d * d) << 32) | (u32)below;
+            row_ptr[CY] = carry;
+            meta[0] = carry;
+            meta[1] = lcarry;
         }
-        if (nxt < last)
+    }
+}
+
+__global__ void k_col_fill(const u32* __restrict__ colmask, const int* __restrict__ row_ptr, int CY, int nw,
+                           int* __restrict__ col_x, int* __restrict__ col_line)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CY * nw)
+        return;
+    const int cy = i / nw, w = i - cy * nw;
+    u32 word = colmask[i];
+    if (!word)
+        return;
+    int o = row_ptr[cy];
+    for (int k = 0; k < w; ++k)
+        o += __popc(colmask[(size_t)cy * nw + k]);
+    while (word)
+    {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const int cx = 32 * w + b;
+        col_x[o] = cx;
+        col_line[o] = cx * CY + cy; // index into line_ptr (vc_sites.cu: columns are numbered cx * CY + cy)
+        ++o;
+    }
+}
+
+// ---- pass Z --------------------------------------------------------------------------------------------
+// One warp per column and 32 planes at a time: lane = plane.  The column's sorted list (cz << 32 | id) is
+// searched per lane (binary search: a rod's column holds hundreds of sites, most columns < 8).
+__global__ void __launch_bounds__(128)
+    k_pass_z(const int* __restrict__ line_ptr, const u64* __restrict__ ent, const int* __restrict__ col_line,
+             const int* __restrict__ meta, u64* __restrict__ G1c, int zb, int pz)
+{
+    const int ncol = meta[0];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncol; ci += nwarps)
+    {
+        const int l = col_line[ci];
+        const int first = line_ptr[l], last = line_ptr[l + 1];
+        u64* out = G1c + (size_t)ci * pz;
+        for (int v = lane; v < pz; v += 32)
         {
-            int d = 2 * ((int)(above >> 32) - vz) - 1;
-            u64 H2 = ((u64)(u32)(d * d) << 32) | (u32)above;
-            H = H2 < H ? H2 : H;
+            const int vz = zb + v;
+            int lo = first, hi = last; // first entry with cz > vz
+            while (lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                if ((int)(ent[mid] >> 32) <= vz)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            __stcs(out + v, vc_nearest_on_zline(ent, first, last, lo - 1, vz));
         }
-        __stcs(out, H);
     }
 }
 
 // ---- envelope stack storage on the device ----------------------------------------------------------
-// The entries of a line's stack below the two in registers.  The upper SR_R of them sit in a
-// per-thread ring in shared memory (slot = depth mod SR_R, threads interleaved so a warp's accesses
-// are conflict free); what falls out at the bottom is spilled to the line's own contiguous array in
-// global memory (8-byte packed entries: consecutive depths of a thread share a 32-byte sector).
-//   forward scan : push = one STS (+ one fire-and-forget STG when the ring is full); a pop reads the
-//                  ring (LDS) and touches global memory only on underflow.
-//   backward scan: the stack is drained strictly downwards and nothing is pushed any more, so the
-//                  slot a pop frees is refilled at once with the entry SR_R below it by an
-//                  asynchronous copy (cp.async, global -> shared, no register in between).  Each drain
-//                  commits exactly one copy group, so `wait_group SR_R-1` before reading a slot is
+// Entries are 16 bytes (g, id, p, start): one LDS.128 / STS.128, nothing to pack.  The top of the stack lives
+// in registers; of the entries below it the upper SR_R sit in a per-thread ring in shared memory (slot =
+// depth mod SR_R, threads interleaved: conflict free whatever the depths), what falls out at the bottom is
+// spilled to the line's own contiguous array in global memory.
+//   forward scan : push = one STS (+ one STG when the ring is full); a pop reads the ring (LDS) and touches
+//                  global memory only on underflow.
+//   backward scan: the stack is drained strictly downwards, so the slot a pop frees is refilled at once with
+//                  the entry SR_R below it by an asynchronous copy (cp.async 16 B, global -> shared).  Each
+//                  drain commits exactly one copy group, so `wait_group SR_R-1` before reading a slot is
 //                  precisely "the copy issued SR_R drains ago has landed": a pop never waits for HBM.
 #ifndef SR_R
 #define SR_R 8
 #endif
 struct StackRing
 {
-    u64* ring; // this thread's slot 0; slot i at ring[i * nthr]
-    u64* glob; // this line's spill array
+    uint4* ring; // this thread's slot 0; slot i at ring[i * nthr]
+    uint4* glob; // this line's spill array
     int nthr;
-    int lo;    // depths >= lo are in the ring, depths < lo only in global memory
+    int lo; // depths >= lo are in the ring, depths < lo only in global memory
 
-    __device__ __forceinline__ u64& slot(int d) { return ring[(d & (SR_R - 1)) * nthr]; }
-    __device__ __forceinline__ void store(int d, u64 e)
+    static __device__ __forceinline__ uint4 pack(const vc_ent& e) { return make_uint4((u32)e.g, e.id, (u32)e.p, (u32)e.start); }
+    static __device__ __forceinline__ vc_ent unpack(const uint4& v)
+    {
+        vc_ent e;
+        e.g = (int)v.x;
+        e.id = v.y;
+        e.p = (int)v.z;
+        e.start = (int)v.w;
+        return e;
+    }
+    __device__ __forceinline__ uint4& slot(int d) { return ring[(d & (SR_R - 1)) * nthr]; }
+    __device__ __forceinline__ void store(int d, const vc_ent& e)
     {
         if (d - lo >= SR_R)
         { // ring full: depth lo lives in the slot depth d is about to take
             glob[lo] = slot(lo);
             ++lo;
         }
-        slot(d) = e;
+        slot(d) = pack(e);
     }
-    __device__ __forceinline__ u64 load(int d)
+    __device__ __forceinline__ vc_ent load(int d)
     {
         if (d >= lo)
-            return slot(d);
+            return unpack(slot(d));
         lo = d; // underflow: the ring is empty from here on
-        return glob[d];
+        return unpack(glob[d]);
     }
     __device__ __forceinline__ void copy_in(int d)
     {
         unsigned dst = (unsigned)__cvta_generic_to_shared(&slot(d));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(glob + d) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(glob + d) : "memory");
     }
     __device__ __forceinline__ void begin_drain(int dtop)
     {
@@ -112,122 +189,142 @@ struct StackRing
             copy_in(d);
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
-    __device__ __forceinline__ u64 drain(int d)
+    __device__ __forceinline__ vc_ent drain(int d)
     {
         asm volatile("cp.async.wait_group %0;" ::"n"(SR_R - 1) : "memory");
-        u64 e = slot(d);
+        const uint4 e = slot(d);
         if (d - SR_R >= 0)
             copy_in(d - SR_R);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        return e;
+        return unpack(e);
     }
 };
 
-// ---- passes X and Y ------------------------------------------------------------------------------
-// TRANSPOSE = true  (pass X): line g = (vz, cy); input G1 + vz*CX*CY + cy, stride CY; the outputs of
-//   32 lines x XY_TW targets are staged in shared memory and written as rows of XY_TW*8 = 128 bytes
-//   of G2[g][vx].
-// TRANSPOSE = false (pass Y): line g = (vz, vx); input G2 + vz*CY*nx + vx, stride nx; outputs go
-//   straight to id/d2x4[(vz*ny + vy)*nx + vx], coalesced across the warp.
-// Both are capped at 64 registers so that 32 warps are resident per SM.
-#define XY_THREADS_T 128 // pass X: 4 warps x 4.25 KB of transpose tile
-#define XY_THREADS_D 256 // pass Y
-#define XY_TW 16         // targets per transposed store burst
-#ifndef XY_MINB_T
-#define XY_MINB_T 8 // resident blocks per SM the register allocation must allow (pass X / pass Y)
-#define XY_MINB_D 4
+// ---- passes X and Y ------------------------------------------------------------------------------------
+#define XY_THREADS 128
+#define XY_TW 16 // pass X: targets per transposed store burst (rows of XY_TW * 8 = 128 bytes)
+#ifndef XY_MINB
+#define XY_MINB 8 // resident blocks per SM the register allocation must allow
 #endif
-template <bool TRANSPOSE>
-__global__ void __launch_bounds__(TRANSPOSE ? XY_THREADS_T : XY_THREADS_D, TRANSPOSE ? XY_MINB_T : XY_MINB_D)
-    k_pass_xy(const u64* __restrict__ in, u64* __restrict__ G2, int* __restrict__ id_out, u32* __restrict__ d2_out,
-              u64* __restrict__ stack, long nlines_total, int lines_per_plane, long in_plane_stride, long in_stride,
-              int ncand, int ntgt, const u32* __restrict__ colmask)
+#define ST_STRIDE(c) ((size_t)((c)->nx > (c)->ny ? (c)->nx : (c)->ny) + 2) // spill entries per line
+
+// pass X: warp = (live row r, group of 32 planes); lane = plane.  Outputs are staged per warp in shared
+// memory and written as rows of 128 bytes of G2c[plane][r][vx].
+__global__ void __launch_bounds__(XY_THREADS, XY_MINB)
+    k_pass_x(const u64* __restrict__ G1c, u64* __restrict__ G2c, uint4* __restrict__ spill, const int* __restrict__ row_ptr,
+             const int* __restrict__ live_row, const int* __restrict__ col_x, const int* __restrict__ meta, int pz, int ngroups,
+             int nx, size_t spill_stride, const double* __restrict__ rcp8w)
 {
-    constexpr int NTHR = TRANSPOSE ? XY_THREADS_T : XY_THREADS_D;
-    __shared__ u64 tile[TRANSPOSE ? XY_THREADS_T / 32 : 1][TRANSPOSE ? 32 : 1][TRANSPOSE ? XY_TW + 1 : 1];
-    __shared__ u64 rings[SR_R * NTHR];
-    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ u64 tile[XY_THREADS / 32][32][XY_TW + 1];
+    __shared__ uint4 rings[SR_R * XY_THREADS];
+    const int nlive = meta[1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * (XY_THREADS / 32) + warp;
+    const int r = w / ngroups, grp = w - r * ngroups;
+    if (r >= nlive)
+        return; // warp-uniform
+    const int cy = live_row[r], c0 = row_ptr[cy], nc = row_ptr[cy + 1] - c0;
+    const int v = grp * 32 + lane; // plane of this lane inside the chunk
+    const bool valid = v < pz;
     StackRing stk;
     stk.ring = rings + threadIdx.x;
-    stk.glob = stack + (size_t)g * (size_t)(ncand + 1); // this line's own contiguous spill array
-    stk.nthr = NTHR;
+    stk.glob = spill + ((size_t)r * pz + (valid ? v : 0)) * spill_stride;
+    stk.nthr = XY_THREADS;
     stk.lo = 0;
-    const bool valid = g < nlines_total;
-    const long plane = valid ? g / lines_per_plane : 0;
-    const int within = valid ? (int)(g - plane * lines_per_plane) : 0;
-    const u64* src = in + plane * in_plane_stride + within;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long gwarp = g - lane;
-
-    if (TRANSPOSE)
-    {
-        const int rsub = lane / XY_TW, col = lane % XY_TW; // a store instruction covers 32/XY_TW rows
-        vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stk,
-                         [&](int t, u32 V, u32 id)
-                         {
-                             tile[warp][lane][t % XY_TW] = ((u64)V << 32) | id;
-                             if ((t % XY_TW) == 0)
-                             {
-                                 __syncwarp();
-                                 const bool colok = t + col < ntgt;
-                                 u64* dst = G2 + (gwarp + rsub) * (long)ntgt + t + col;
+    const int rsub = lane / XY_TW, col = lane % XY_TW; // a store instruction covers 32 / XY_TW rows
+    const int v0 = grp * 32;
+    vc_envelope_pruned(G1c + (size_t)c0 * pz + v, (long)pz, col_x + c0, valid ? nc : 0, nx, stk,
+                 [&](int t, u32 V, u32 id)
+                 {
+                     tile[warp][lane][t % XY_TW] = ((u64)V << 32) | id;
+                     if ((t % XY_TW) == 0)
+                     {
+                         __syncwarp();
+                         const bool colok = t + col < nx;
+                         u64* dst = G2c + ((size_t)(v0 + rsub) * nlive + r) * nx + t + col;
 #pragma unroll 4
-                                 for (int r = rsub; r < 32; r += 32 / XY_TW, dst += (long)(32 / XY_TW) * ntgt)
-                                     if (colok && gwarp + r < nlines_total)
-                                         *dst = tile[warp][r][col];
-                                 __syncwarp();
-                             }
-                         },
-                         colmask ? colmask + (size_t)within * (size_t)((ncand + 31) >> 5) : nullptr);
-    }
-    else
-    {
-        const long last = plane * (long)ntgt * lines_per_plane + within + (long)(ntgt - 1) * lines_per_plane;
-        int* pid = id_out + last;
-        u32* pd2 = d2_out + last;
-        vc_envelope_line(src, in_stride, valid ? ncand : 0, ntgt, stk,
-                         [&](int t, u32 V, u32 id)
-                         { // targets arrive as ntgt-1 .. 0
-                             if (valid)
-                             {
-                                 __stcs(pid, (int)id);
-                                 __stcs(pd2, V);
-                             }
-                             pid -= lines_per_plane;
-                             pd2 -= lines_per_plane;
-                         });
-    }
+                         for (int rr = rsub; rr < 32; rr += 32 / XY_TW, dst += (size_t)(32 / XY_TW) * nlive * nx)
+                             if (colok && v0 + rr < pz)
+                                 *dst = tile[warp][rr][col];
+                         __syncwarp();
+                     }
+                 });
 }
 
-// scratch for the envelope stacks: one region per z chunk of the pipeline (chunks run concurrently),
-// a region holds (planes + halo) x lines x (candidates + 1) packed 8-byte entries
+// pass Y: line = (plane, vx), lanes along vx; candidates = the live rows; writes id / 4d^2 coalesced.
+__global__ void __launch_bounds__(XY_THREADS, XY_MINB)
+    k_pass_y(const u64* __restrict__ G2c, int* __restrict__ id_out, u32* __restrict__ d2_out, uint4* __restrict__ spill,
+             const int* __restrict__ live_row, const int* __restrict__ meta, long nlines, int nx, int ny, size_t spill_stride,
+             const double* __restrict__ rcp8w)
+{
+    __shared__ uint4 rings[SR_R * XY_THREADS];
+    const int nlive = meta[1];
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g < nlines;
+    const long plane = valid ? g / nx : 0;
+    const int vx = valid ? (int)(g - plane * nx) : 0;
+    StackRing stk;
+    stk.ring = rings + threadIdx.x;
+    stk.glob = spill + (size_t)(valid ? g : 0) * spill_stride;
+    stk.nthr = XY_THREADS;
+    stk.lo = 0;
+    const long last = (plane * ny + (ny - 1)) * (long)nx + vx;
+    int* pid = id_out + last;
+    u32* pd2 = d2_out + last;
+    vc_envelope_pruned(G2c + (size_t)plane * nlive * nx + vx, (long)nx, live_row, valid ? nlive : 0, ny, stk,
+                 [&](int t, u32 V, u32 id)
+                 { // targets arrive as ny-1 .. 0
+                     if (valid)
+                     {
+                         __stcs(pid, (int)id);
+                         __stcs(pd2, V);
+                     }
+                     pid -= nx;
+                     pd2 -= nx;
+                 },
+                 rcp8w);
+}
+
+__global__ void k_rcp_table(double* t, int n)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n)
+        t[w] = w ? 1.0 / (8.0 * (double)w) : 0.0;
+}
+
+// scratch for the envelope stacks: one region per z chunk of the pipeline (chunks run concurrently), a region
+// holds planes x lines x ST_STRIDE 16-byte entries (touched only as deep as a stack outgrows its ring)
 static size_t stack_region_entries(const vc_ctx* c, int planes)
 {
-    const size_t CX = c->nx + 1, CY = c->ny + 1;
-    const size_t a = CY * (CX + 1), b = (size_t)c->nx * (CY + 1); // pass X, pass Y entries per plane
-    return (size_t)planes * (a > b ? a : b);
+    const size_t CY = c->ny + 1;
+    const size_t lines = CY > (size_t)c->nx ? CY : (size_t)c->nx; // pass X: <= CY live rows, pass Y: nx lines per plane
+    return (size_t)planes * lines * ST_STRIDE(c);
 }
 
-static void launch_passes(vc_ctx* c, int zb, int nplanes, u64* stack)
+// compact column tables of the current site set (once per site set: st_finalize_sites clears edt_cols_ready)
+static int edt_columns(vc_ctx* c)
 {
-    const int CX = c->nx + 1, CY = c->ny + 1;
-    const size_t off = (size_t)(zb - c->z0);
-    u64* g1 = c->g1.as<u64>() + off * CX * CY;
-    u64* g2 = c->g2.as<u64>() + off * CY * c->nx;
-    // pass X: lines (vz, cy)
+    const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
+    const size_t ncolcap = (size_t)CX * CY;
+    if (!c->rcp8w.p)
     {
-        long nlines = (long)nplanes * CY;
-        VC_LAUNCH(c, "edt_pass_x", k_pass_xy<true>, vc_blocks((size_t)nlines, XY_THREADS_T), XY_THREADS_T, 0, g1, g2,
-                  (int*)nullptr, (u32*)nullptr, stack, nlines, CY, (long)CX * CY, (long)CY, CX, c->nx,
-                  c->colmask.as<u32>());
+        VC_CUDA(c, c->rcp8w.ensure(2052 * sizeof(double)));
+        VC_LAUNCH(c, "edt_rcp_table", k_rcp_table, vc_blocks(2052, 256), 256, 0, c->rcp8w.as<double>(), 2052);
     }
-    // pass Y: lines (vz, vx)
-    {
-        long nlines = (long)nplanes * c->nx;
-        VC_LAUNCH(c, "edt_pass_y", k_pass_xy<false>, vc_blocks((size_t)nlines, XY_THREADS_D), XY_THREADS_D, 0, g2,
-                  (u64*)nullptr, c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, stack, nlines,
-                  c->nx, (long)CY * c->nx, (long)c->nx, CY, c->ny, (const u32*)nullptr);
-    }
+    if (c->edt_cols_ready)
+        return VC_OK;
+    VC_CUDA(c, c->row_ptr.ensure((size_t)(CY + 2) * 4));
+    VC_CUDA(c, c->live_row.ensure((size_t)(CY + 2) * 4));
+    VC_CUDA(c, c->edt_meta.ensure(64));
+    const size_t cap = (size_t)c->nsites < ncolcap ? (size_t)c->nsites : ncolcap;
+    VC_CUDA(c, c->col_x.ensure((cap + 1) * 4));
+    VC_CUDA(c, c->col_line.ensure((cap + 1) * 4));
+    VC_LAUNCH(c, "edt_columns", k_col_rows, 1, 1024, 0, c->colmask.as<u32>(), CY, nw, c->row_ptr.as<int>(), c->live_row.as<int>(),
+              c->edt_meta.as<int>());
+    VC_LAUNCH(c, "edt_columns", k_col_fill, vc_blocks((size_t)CY * nw, 256), 256, 0, c->colmask.as<u32>(), c->row_ptr.as<int>(), CY,
+              nw, c->col_x.as<int>(), c->col_line.as<int>());
+    c->edt_cols_ready = true;
+    return VC_OK;
 }
 
 // buffers of the transform; `regions` stack regions of `region_planes` planes each
@@ -240,11 +337,12 @@ static int edt_alloc(vc_ctx* c, int regions, int region_planes)
     const size_t nv = (size_t)c->nx * c->ny * nplanes;
     if ((CX > CY ? CX : CY) > 2049)
         return vc_fail(c, VC_ERR_UNSUPPORTED, "grid side above 2048 is not supported by the dense transform");
+    // G1c of a chunk: [columns][planes] <= CX*CY columns; G2c: [planes][live rows][nx] <= CY rows: the dense bounds
     VC_CUDA(c, c->g1.ensure((size_t)nplanes * CX * CY * 8));
     VC_CUDA(c, c->g2.ensure((size_t)nplanes * CY * c->nx * 8));
     VC_CUDA(c, c->id.ensure(nv * 4));
     VC_CUDA(c, c->d2.ensure(nv * 4));
-    VC_CUDA(c, c->stk.ensure((size_t)regions * stack_region_entries(c, region_planes) * sizeof(u64)));
+    VC_CUDA(c, c->stk.ensure((size_t)regions * stack_region_entries(c, region_planes) * sizeof(uint4)));
     return VC_OK;
 }
 
@@ -252,17 +350,34 @@ static int edt_alloc(vc_ctx* c, int regions, int region_planes)
 int edt_range(vc_ctx* c, int zb, int ze, int region, int region_planes)
 {
     const int CX = c->nx + 1, CY = c->ny + 1;
-    const int nplanes = ze - zb;
-    const int nlines = CX * CY;
-    VC_LAUNCH(c, "edt_pass_z", k_pass_z, dim3(vc_blocks((size_t)nlines, 256), (nplanes + PZ_CHUNK - 1) / PZ_CHUNK), 256, 0,
-              c->line_ptr.as<int>(), c->line_ent.as<u64>(), c->g1.as<u64>() + (size_t)(zb - c->z0) * nlines, nlines, zb, ze);
-    launch_passes(c, zb, nplanes, c->stk.as<u64>() + (size_t)region * stack_region_entries(c, region_planes));
+    const int pz = ze - zb;
+    if (pz <= 0)
+        return VC_OK;
+    const size_t off = (size_t)(zb - c->z0);
+    u64* g1 = c->g1.as<u64>() + off * CX * CY;
+    u64* g2 = c->g2.as<u64>() + off * CY * c->nx;
+    uint4* spill = c->stk.as<uint4>() + (size_t)region * stack_region_entries(c, region_planes);
+    const int* meta = c->edt_meta.as<int>();
+    if (c->nsites > 0)
+    {
+        VC_LAUNCH(c, "edt_pass_z", k_pass_z, c->sm_count * 8, 128, 0, c->line_ptr.as<int>(), c->line_ent.as<u64>(),
+                  c->col_line.as<int>(), meta, g1, zb, pz);
+        const int ngroups = (pz + 31) / 32;
+        const size_t warps = (size_t)CY * ngroups; // warps of rows that are not live leave at once
+        VC_LAUNCH(c, "edt_pass_x", k_pass_x, vc_blocks(warps, XY_THREADS / 32), XY_THREADS, 0, g1, g2, spill, c->row_ptr.as<int>(),
+                  c->live_row.as<int>(), c->col_x.as<int>(), meta, pz, ngroups, c->nx, ST_STRIDE(c), c->rcp8w.as<double>());
+    }
+    const long nlines = (long)pz * c->nx;
+    VC_LAUNCH(c, "edt_pass_y", k_pass_y, vc_blocks((size_t)nlines, XY_THREADS), XY_THREADS, 0, g2,
+              c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, spill, c->live_row.as<int>(), meta, nlines,
+              c->nx, c->ny, ST_STRIDE(c), c->rcp8w.as<double>());
     return VC_OK;
 }
 
 int st_closest_lattice(vc_ctx* c)
 {
     VC_TRY(edt_alloc(c, 1, c->zc - c->z0));
+    VC_TRY(edt_columns(c));
     VC_TRY(edt_range(c, c->z0, c->zc, 0, c->zc - c->z0));
     VC_CUDA(c, cudaGetLastError());
     c->have_closest = true;
@@ -270,12 +385,13 @@ int st_closest_lattice(vc_ctx* c)
     return VC_OK;
 }
 
-// Closest sites + measures of the whole slab as a pipeline over z chunks.  Chunk k = planes
-// [zb, ze): its three transform passes cover [zb, ze+1) -- the halo plane its measures reach up to
-// is recomputed rather than waited for (the same rule as between GPUs; chunk
-// k+1 stores the identical values again) -- then its measures run on the same worker stream.
-// Chunks are dealt round-robin to the worker streams, so there is no device-wide barrier between
-// the passes: the tail of one chunk's stage overlaps whatever the other streams are running.
+// Closest sites + measures of the whole slab as a pipeline over z chunks.  The transform ranges [zb, ze) of
+// the chunks partition the closest planes [z0, zc); the measures of chunk k cover the planes [zb - 1, ze - 1)
+// (from z0 for the first chunk, up to z1 for the last): the cells of plane z read the ids of plane z + 1, so a
+// chunk's measures need its own transform and the LAST plane of the chunk before it -- one event wait across
+// worker streams, no plane is transformed twice and no two streams ever write the same address.
+// Chunks are dealt round-robin to the worker streams, so there is no device-wide barrier between the passes:
+// the tail of one chunk's stage overlaps whatever the other streams are running.
 // With profiling on, everything runs on the main stream so per-kernel event times stay meaningful.
 int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
 {
@@ -286,23 +402,25 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
     }
     const int nplanes_all = c->zc - c->z0;
     const int nw = c->profiling ? 0 : c->nworkers;
-    // chunk height: >= 32k lines per launch keeps a chunk's kernels efficient on their own (measured:
-    // 64 planes at 512^2, profiles/), VC_ZCHUNK overrides; one chunk when profiling
+    // chunk height: a multiple of 32 planes (pass X puts 32 planes in a warp) with >= 32k lines per launch so that
+    // a chunk's kernels are efficient on their own (64 planes at 512^2), VC_ZCHUNK overrides; one chunk when profiling
     int zchunk = c->zchunk;
     if (zchunk <= 0)
     {
         const int side = c->nx < c->ny ? c->nx : c->ny;
         zchunk = (32768 + side - 1) / side;
-        zchunk = zchunk < 8 ? 8 : zchunk;
-        // ... and no more chunks than about one per worker stream: with many more (1024^3 on one GPU: 32) the halo
-        // recompute and the launch count cost more than the overlap gives (30.6 vs 27.6 ms unpipelined, measured)
-        const int per_worker = (nplanes_all + (nw > 0 ? nw : 1) - 1) / (nw > 0 ? nw : 1);
+        zchunk = ((zchunk < 32 ? 32 : zchunk) + 31) / 32 * 32;
+        // ... and no more chunks than about one per worker stream: with many more (1024^3 on one GPU: 32) the
+        // launch count costs more than the overlap gives
+        const int per_worker = ((nplanes_all + (nw > 0 ? nw : 1) - 1) / (nw > 0 ? nw : 1) + 31) / 32 * 32;
         zchunk = zchunk < per_worker ? per_worker : zchunk;
     }
     if (!nw || zchunk > nplanes_all)
         zchunk = nplanes_all;
-    const int nchunks = (nplanes_all + zchunk - 1) / zchunk;
-    VC_TRY(edt_alloc(c, nchunks, zchunk + 1));
+    // the last chunk takes the remainder (a slab's halo plane, for one) instead of becoming a launch of its own
+    const int nchunks = nplanes_all / zchunk > 1 ? nplanes_all / zchunk : 1;
+    const int region_planes = nplanes_all - (nchunks - 1) * zchunk;
+    VC_TRY(edt_alloc(c, nchunks, region_planes));
     if (!c->have_inside)
         return vc_fail(c, VC_ERR_STATE, "measures need vc_classify_grid");
     if (c->zhi < c->zc)
@@ -310,24 +428,40 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
     const bool dense_measures = !c->skip_dense_measures;
     if (dense_measures)
         VC_TRY(measures_alloc(c, want_radius));
+    VC_TRY(edt_columns(c)); // on the main stream, before the fork
+    while ((int)c->ev_chunk.size() < nchunks)
+    {
+        cudaEvent_t e = nullptr;
+        VC_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_chunk.push_back(e);
+    }
     if (nw)
     {
         VC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
         for (int i = 0; i < nw; ++i)
             VC_CUDA(c, cudaStreamWaitEvent(c->workers[i], c->ev_fork, 0));
     }
-    int k = 0, status = VC_OK;
-    for (int zb = c->z0; zb < c->zc && status == VC_OK; zb += zchunk, ++k)
+    int status = VC_OK;
+    for (int k = 0; k < nchunks && status == VC_OK; ++k)
     {
-        const int ze = zb + zchunk < c->zc ? zb + zchunk : c->zc;
-        const int zh = ze < c->zc ? ze + 1 : ze; // transform range incl. the halo plane
+        const int zb = c->z0 + k * zchunk;
+        const int ze = k == nchunks - 1 ? c->zc : zb + zchunk;
         c->cur = nw ? c->workers[k % nw] : c->stream;
-        status = edt_range(c, zb, zh, k, zchunk + 1);
-        const int me = ze < c->z1 ? ze : c->z1;
-        if (status == VC_OK && zb < me && dense_measures)
-            status = measures_range(c, zb, me, want_radius);
-        if (status == VC_OK && zb < me && c->chunk_hook)
-            status = c->chunk_hook(zb, me); // e.g. compaction + device-to-host copy of this chunk's records
+        status = edt_range(c, zb, ze, k, region_planes);
+        if (status != VC_OK)
+            break;
+        if (nw)
+        {
+            VC_CUDA(c, cudaEventRecord(c->ev_chunk[k], c->cur));
+            if (k > 0)
+                VC_CUDA(c, cudaStreamWaitEvent(c->cur, c->ev_chunk[k - 1], 0));
+        }
+        const int ma = k == 0 ? c->z0 : zb - 1;
+        const int mb = ze >= c->zc ? c->z1 : ze - 1;
+        if (ma < mb && dense_measures)
+            status = measures_range(c, ma, mb, want_radius);
+        if (status == VC_OK && ma < mb && c->chunk_hook)
+            status = c->chunk_hook(ma, mb); // e.g. compaction + device-to-host copy of this chunk's records
     }
     c->cur = c->stream;
     if (nw)

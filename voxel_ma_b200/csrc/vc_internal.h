@@ -97,7 +97,12 @@ struct vc_ctx
     DevBuf colmask;            // u32[ny+1][(nx+32)/32] bit rows: column (cx,cy) has sites (pass Z writes, pass X reads only those)
     // transform scratch + results
     DevBuf g1, g2, id, d2, edge3, face3, cube, radius;
-    DevBuf stk; // envelope stacks of the transform passes (packed u64 per line and depth)
+    DevBuf stk; // spill space of the envelope stacks of the transform passes (16-byte entries per line and depth)
+    // compact columns of the site set (vc_edt.cu): row_ptr[cy] = first column of row cy, col_x / col_line per column,
+    // live_row = rows that hold columns, edt_meta = {#columns, #live rows}; rcp8w[w] = 1 / (8w) for vc_sep
+    DevBuf row_ptr, live_row, col_x, col_line, edt_meta, rcp8w;
+    bool edt_cols_ready = false;
+    std::vector<cudaEvent_t> ev_chunk; // "transform of z chunk k done" (the next chunk's measures wait for it)
     // sort scratch
     DevBuf sk0, sk1, sv0, sv1, shist;
     int coop_sort = -1; // blocks of the single-launch cooperative radix sort that fit the device (0: launch per phase)

@@ -1175,9 +1175,10 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
 {
     const int nlines = (c->nx + 1) * (c->ny + 1);
     if (n > (int64_t)VC_MAX_SITE_ID + 1)
-        return vc_fail(c, VC_ERR_UNSUPPORTED, "more than 2^26 sites: ids no longer fit the transform's packed stack entries");
+        return vc_fail(c, VC_ERR_UNSUPPORTED, "more than 2^25 sites: ids no longer fit the packed 25-bit id fields of the dense path");
     c->nsites = n;
     c->lattice = true;
+    c->edt_cols_ready = false; // the transform's compact column tables belong to the previous site set
     c->cl_dim[0] = 0; // any cell list of a previous site set is stale
     VC_CUDA(c, c->site_key.ensure((size_t)(n + 1) * 8));
     VC_CUDA(c, c->site_corner.ensure((size_t)(n + 1) * 8));
