@@ -158,7 +158,8 @@ extern "C"
                 const int cy = liverow[r], c0 = rowptr[cy], nc = rowptr[cy + 1] - c0;
                 vc_u64* row = &G2[((size_t)vz * nlive + r) * nx];
                 vc_pstack_array stk{stkv.data()};
-                vc_envelope_pruned(&G1[(size_t)c0 * nzs + vz], (long)nzs, &colx[c0], nc, nx, stk,
+                vc_psource_array src{&G1[(size_t)c0 * nzs + vz], (long)nzs, &colx[c0]};
+                vc_envelope_pruned(src, nc, nx, stk,
                                    [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; }, rcp.data());
                 st[0]++, st[1] += nc, st[2] += stk.npop, st[3] = std::max<int64_t>(st[3], stk.maxdepth + 1);
                 if (depth_hist)
@@ -169,7 +170,8 @@ extern "C"
             for (int vx = 0; vx < nx; ++vx)
             {
                 vc_pstack_array stk{stkv.data()};
-                vc_envelope_pruned(&G2[(size_t)vz * nlive * nx + vx], (long)nx, liverow.data(), nlive, ny, stk,
+                vc_psource_array src{&G2[(size_t)vz * nlive * nx + vx], (long)nx, liverow.data()};
+                vc_envelope_pruned(src, nlive, ny, stk,
                                    [&](int t, uint32_t V, uint32_t id)
                                    {
                                        size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
@@ -199,7 +201,8 @@ extern "C"
                 h.push_back(in[j]), pos.push_back(j);
         std::vector<vc_ent> stkv(ncand + 2);
         vc_pstack_array stk{stkv.data()};
-        vc_envelope_pruned(h.data(), 1L, pos.data(), (int)h.size(), ntgt, stk,
+        vc_psource_array src{h.data(), 1L, pos.data()};
+        vc_envelope_pruned(src, (int)h.size(), ntgt, stk,
                            [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; }, rcp.data());
     }
 

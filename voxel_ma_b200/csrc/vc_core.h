@@ -253,10 +253,13 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
 // The one division is done in double: |N| < 2^28, divisor 8w <= 2^14; the true quotient of (N + 0.5) / (8w) is
 // at least 2^-15 away from every integer and the product with the rounded reciprocal is off by < 2^-24, so the
 // floor is exact (tests/test_host_core.py sweeps every divisor).  rcp8w[w] = 1.0 / (8 w), w in [1, 2048].
-VC_HD int vc_sep(int dg, int c, int w, const double* __restrict__ rcp8w)
+template <class Rcp>
+VC_HD int vc_sep(int dg, int c, int w, const Rcp& rcp8w)
 {
     const int N = dg + c - 1 + 4 * w;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(WHATIF_NODIV) // timing experiment only: wrong results
+    return N >> 3;
+#elif defined(__CUDA_ARCH__)
     return __double2int_rd(((double)N + 0.5) * rcp8w[w]);
 #else
     double qd = ((double)N + 0.5) * rcp8w[w];
@@ -303,94 +306,92 @@ struct vc_pstack_array
     VC_HD vc_ent drain(int d) { return a[d]; }
 };
 
-// One line.  src + k * stride = word (4 D << 32 | id) of the k-th LIVE candidate (all finite), pos[k] = its position
-// on the candidate axis, ascending -- on the device pos is the same array for every lane of a warp, so the scan's
-// control flow only diverges in the pops.  The fetch is software-pipelined VC_EPF candidates ahead.
-// emit(t, V, id) is called for t = ntgt-1 .. 0 (all-ones when the line has no candidate).
-#ifndef VC_EPF
-#define VC_EPF 4
-#endif
-#if defined(__CUDA_ARCH__)
-#define VC_LOAD_POS(p) __ldg(p)
+// Candidate source of a line: get(k, H, p) hands out the k-th LIVE candidate (k ascending, every k exactly once): its
+// word H = 4 D << 32 | id (finite) and its position p on the candidate axis (ascending).  On the device the
+// positions are the same for every lane of a warp, so the scan's control flow only diverges in the pops, and the
+// words are staged through shared memory several candidates ahead (vc_edt.cu: CandStage); the CPU harness reads
+// plain arrays.
+struct vc_psource_array
+{
+    const vc_u64* src; // word of candidate k at src[k * stride]
+    long stride;
+    const int* pos;
+    VC_HD void get(int k, vc_u64& H, int& p) const
+    {
+        H = src[(long)k * stride];
+        p = pos[k];
+    }
+};
+
+#if defined(__CUDA_ARCH__) && !defined(VC_NO_RECONVERGE)
+#define VC_LANES(m) const unsigned m = __ballot_sync(__activemask(), ncand > 0)
+#define VC_RECONVERGE(m) __syncwarp(m)
 #else
-#define VC_LOAD_POS(p) (*(p))
+#define VC_LANES(m) (void)0
+#define VC_RECONVERGE(m) (void)0
 #endif
-template <class Stack, class Emit>
-VC_HD void vc_envelope_pruned(const vc_u64* __restrict__ src, long stride, const int* __restrict__ pos, int ncand, int ntgt,
-                              Stack& stk, Emit emit, const double* __restrict__ rcp8w)
+
+// One line.  emit(t, V, id) is called for t = ntgt-1 .. 0 (all-ones when the line has no candidate).
+template <class Source, class Stack, class Emit, class Rcp>
+VC_HD void vc_envelope_pruned(Source& src, int ncand, int ntgt, Stack& stk, Emit emit, const Rcp& rcp8w)
 {
     int q = -1; // depth of the top (registers); depths 0 .. q-1 are in stk
     int gt = 0, pt = 0, st = 0, at = 0; // at = 4 (2 st + 1)
     uint32_t idt = 0;
-    vc_u64 hb[VC_EPF];
-    int pb[VC_EPF];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < VC_EPF; ++i)
-        if (i < ncand)
-        {
-            hb[i] = VC_LOAD_STREAM(src + (long)i * stride);
-            pb[i] = VC_LOAD_POS(pos + i);
-        }
-    for (int k0 = 0; k0 < ncand; k0 += VC_EPF)
+    VC_LANES(lanes); // the lanes that scan a line with candidates (same count for all of them)
+    for (int k = 0; k < ncand; ++k)
     {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 0; i < VC_EPF; ++i)
-        {
-            const int k = k0 + i;
-            if (k >= ncand)
+        vc_u64 H;
+        int j;
+        src.get(k, H, j);
+        const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
+        const uint32_t id = (uint32_t)H;
+        while (q >= 0)
+        { // new - top at the top's own start; the top survives iff it still wins there
+            const int diff = (g - gt) - (j - pt) * at;
+            if (diff > 0 || (diff == 0 && id >= idt))
                 break;
-            const vc_u64 H = hb[i];
-            const int j = pb[i];
-            if (k + VC_EPF < ncand)
-            {
-                hb[i] = VC_LOAD_STREAM(src + (long)(k + VC_EPF) * stride);
-                pb[i] = VC_LOAD_POS(pos + k + VC_EPF);
-            }
-            const int g = (int)(uint32_t)(H >> 32) + 4 * j * j;
-            const uint32_t id = (uint32_t)H;
-            while (q >= 0)
-            { // new - top at the top's own start; the top survives iff it still wins there
-                const int diff = (g - gt) - (j - pt) * at;
-                if (diff > 0 || (diff == 0 && id >= idt))
-                    break;
-                --q;
-                if (q >= 0)
-                {
-                    const vc_ent e = stk.load(q);
-                    gt = e.g;
-                    idt = e.id;
-                    pt = e.p;
-                    st = e.start;
-                    at = 8 * st + 4;
-                }
-            }
-            int s = 0;
+            --q;
             if (q >= 0)
             {
-                s = vc_sep(g - gt, id < idt ? 0 : 1, j - pt, rcp8w);
-                if (s >= ntgt)
-                    continue; // never the winner inside the line
-                vc_ent e;
-                e.g = gt;
-                e.id = idt;
-                e.p = pt;
-                e.start = st;
-                stk.store(q, e);
+                const vc_ent e = stk.load(q);
+                gt = e.g;
+                idt = e.id;
+                pt = e.p;
+                st = e.start;
+                at = 8 * st + 4;
             }
-            gt = g;
-            idt = id;
-            pt = j;
-            st = s;
-            at = 8 * s + 4;
-            ++q;
         }
+        VC_RECONVERGE(lanes); // device: the lanes that stopped popping early wait here instead of running ahead alone
+        int s = 0;
+        if (q >= 0)
+        {
+            s = vc_sep(g - gt, id < idt ? 0 : 1, j - pt, rcp8w);
+            if (s >= ntgt)
+                continue; // never the winner inside the line
+            vc_ent e;
+            e.g = gt;
+            e.id = idt;
+            e.p = pt;
+            e.start = st;
+            stk.store(q, e);
+        }
+        gt = g;
+        idt = id;
+        pt = j;
+        st = s;
+        at = 8 * s + 4;
+        ++q;
     }
     // Backward scan: the top is the winner until t == its start.  V(t) = g + x (x - 4p) with x = 2t + 1;
     // V(t-1) = V(t) - m with m = 4 (x - 2p - 1), and m itself falls by 8 per step.
+#if defined(__CUDA_ARCH__) && defined(WHATIF_NOBACK) // timing experiment only
+    if (q > -5)
+    {
+        emit(0, (uint32_t)gt, idt);
+        return;
+    }
+#endif
     stk.begin_drain(q - 1);
     int x = 2 * (ntgt - 1) + 1;
     uint32_t V = (uint32_t)(gt + x * (x - 4 * pt));

@@ -25,7 +25,7 @@
 // meta[0] = number of columns with sites, meta[1] = number of live rows
 __global__ void __launch_bounds__(1024)
     k_col_rows(const u32* __restrict__ colmask, int CY, int nw, int* __restrict__ row_ptr, int* __restrict__ live_row,
-               int* __restrict__ meta)
+               u32* __restrict__ row_mask, int* __restrict__ meta)
 {
     __shared__ int cnt[2052], liv[2052];
     for (int cy = threadIdx.x; cy < CY; cy += blockDim.x)
@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(1024)
                     linc += u;
                 }
             }
+            const u32 lw = __ballot_sync(0xffffffffu, l != 0); // bit cy & 31 of word cy >> 5: row cy is live
+            if (threadIdx.x == 0)
+                row_mask[b >> 5] = lw;
             if (cy < CY)
             {
                 row_ptr[cy] = carry + inc - v;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(1024)
             row_ptr[CY] = carry;
             meta[0] = carry;
             meta[1] = lcarry;
+            row_mask[(CY + 31) >> 5] = 0u; // the word the bitmap walk may read ahead
         }
     }
 }
@@ -129,26 +133,66 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// ---- shared-memory helpers: explicit 32-bit shared addresses, one instruction per access -------------------
+__device__ __forceinline__ uint4 lds128(unsigned a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, const uint4& v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ u64 lds64(unsigned a)
+{
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define XY_THREADS 128
+
 // ---- envelope stack storage on the device ----------------------------------------------------------
 // Entries are 16 bytes (g, id, p, start): one LDS.128 / STS.128, nothing to pack.  The top of the stack lives
 // in registers; of the entries below it the upper SR_R sit in a per-thread ring in shared memory (slot =
 // depth mod SR_R, threads interleaved: conflict free whatever the depths), what falls out at the bottom is
-// spilled to the line's own contiguous array in global memory.
-//   forward scan : push = one STS (+ one STG when the ring is full); a pop reads the ring (LDS) and touches
-//                  global memory only on underflow.
+// spilled to global memory.
+//   forward scan : push = one STS (+ one STG when the ring is full); a pop reads the ring (LDS).  A pop below the
+//                  ring (a long run of pops: the scan has just passed a much closer surface) refills the WHOLE
+//                  ring with the SR_R entries below in one go -- SR_R independent copies, one round trip to L2 /
+//                  HBM per SR_R pops instead of one per pop.
+//   spill layout : the stores of the spill are what bounds these kernels (measured: without them pass Y takes
+//                  0.6 instead of 1.5 ms), so a warp's 32 stacks are INTERLEAVED, [depth][lane] x 16 B: lanes at
+//                  the same depth -- neighbouring lines have nearly the same envelope -- share full 128-byte
+//                  lines, one store instruction then costs 4 wavefronts / 16 full sectors instead of 32 wavefronts
+//                  / 32 half-written sectors of 32 private arrays (and never more than those).
 //   backward scan: the stack is drained strictly downwards, so the slot a pop frees is refilled at once with
 //                  the entry SR_R below it by an asynchronous copy (cp.async 16 B, global -> shared).  Each
 //                  drain commits exactly one copy group, so `wait_group SR_R-1` before reading a slot is
 //                  precisely "the copy issued SR_R drains ago has landed": a pop never waits for HBM.
-#ifndef SR_R
-#define SR_R 8
+#ifndef SR_RX
+#define SR_RX 8 // ring slots per thread, pass X / pass Y
 #endif
+#ifndef SR_RY
+#define SR_RY 8
+#endif
+template <int SR_R>
 struct StackRing
 {
-    uint4* ring; // this thread's slot 0; slot i at ring[i * nthr]
-    uint4* glob; // this line's spill array
-    int nthr;
-    int lo; // depths >= lo are in the ring, depths < lo only in global memory
+    unsigned sbase; // shared address of this thread's slot 0; slot i at sbase + i * XY_THREADS * 16
+    uint4* glob;    // this lane's column of the warp's spill block: depth d at glob[d * 32]
+    int lo;         // depths >= lo are in the ring, depths < lo only in global memory
 
     static __device__ __forceinline__ uint4 pack(const vc_ent& e) { return make_uint4((u32)e.g, e.id, (u32)e.p, (u32)e.start); }
     static __device__ __forceinline__ vc_ent unpack(const uint4& v)
@@ -160,49 +204,134 @@ struct StackRing
         e.start = (int)v.w;
         return e;
     }
-    __device__ __forceinline__ uint4& slot(int d) { return ring[(d & (SR_R - 1)) * nthr]; }
+    __device__ __forceinline__ unsigned slot(int d) const { return sbase + (unsigned)(d & (SR_R - 1)) * (XY_THREADS * 16); }
     __device__ __forceinline__ void store(int d, const vc_ent& e)
     {
         if (d - lo >= SR_R)
         { // ring full: depth lo lives in the slot depth d is about to take
-            glob[lo] = slot(lo);
+#if !defined(WHATIF_NOSPILL) // timing experiments only (results are wrong with these switches)
+            glob[lo * 32] = lds128(slot(lo));
+#endif
             ++lo;
         }
-        slot(d) = pack(e);
+        sts128(slot(d), pack(e));
     }
     __device__ __forceinline__ vc_ent load(int d)
     {
-        if (d >= lo)
-            return unpack(slot(d));
-        lo = d; // underflow: the ring is empty from here on
-        return unpack(glob[d]);
-    }
-    __device__ __forceinline__ void copy_in(int d)
-    {
-        unsigned dst = (unsigned)__cvta_generic_to_shared(&slot(d));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(glob + d) : "memory");
+        if (d < lo)
+        { // below the ring: everything above d is popped, so the ring is free -- fetch depths d-SR_R+1 .. d together
+            const int first = d - SR_R + 1 > 0 ? d - SR_R + 1 : 0;
+#if !defined(WHATIF_NOREFILL)
+            for (int e = first; e <= d; ++e)
+                cp_async16(slot(e), glob + e * 32);
+            cp_commit();
+            cp_wait<0>();
+#endif
+            lo = first;
+        }
+        return unpack(lds128(slot(d)));
     }
     __device__ __forceinline__ void begin_drain(int dtop)
     {
-        int first = dtop - SR_R + 1;
+        const int first = dtop - SR_R + 1;
         for (int d = lo - 1; d >= 0 && d >= first; --d)
-            copy_in(d);
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            cp_async16(slot(d), glob + d * 32);
+        cp_commit();
+        cp_wait<0>();
     }
     __device__ __forceinline__ vc_ent drain(int d)
     {
-        asm volatile("cp.async.wait_group %0;" ::"n"(SR_R - 1) : "memory");
-        const uint4 e = slot(d);
+        cp_wait<SR_R - 1>();
+        const uint4 e = lds128(slot(d));
         if (d - SR_R >= 0)
-            copy_in(d - SR_R);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+            cp_async16(slot(d), glob + (d - SR_R) * 32);
+        cp_commit();
         return unpack(e);
     }
 };
 
+// ---- candidate stream ----------------------------------------------------------------------------------
+// Words: two candidates ahead in registers, ED_PFD candidates ahead in L2 (prefetch.global.L2: no register, no
+// shared memory -- the shared-memory pipe is what bounds these kernels, so the fetch stays out of it).
+// Positions: the candidates of a warp are the set bits of a bitmap that is the same for every lane (pass X: the
+// row's columns, `colmask`; pass Y: the live rows, `row_mask`), walked with ffs -- no load per candidate at all.
+#ifndef ED_PFD
+#define ED_PFD 24
+#endif
+struct CandStream
+{
+    const u64 *gp, *gpf; // word of the next candidate to load / to prefetch
+    long stride;
+    u64 h1, h2;
+    const u32* mw; // next bitmap word
+    u32 word, wnext;
+    int base, ncand;
+    __device__ __forceinline__ void init(const u64* src, long stride_, const u32* mask, int ncand_)
+    {
+        stride = stride_;
+        ncand = ncand_;
+        h1 = ncand > 0 ? VC_LOAD_STREAM(src) : 0ull;
+        h2 = ncand > 1 ? VC_LOAD_STREAM(src + stride) : 0ull;
+        gp = src + 2 * stride;
+        gpf = gp;
+        for (int i = 2; i < ED_PFD && i < ncand; ++i, gpf += stride)
+            VC_PREFETCH_L2(gpf);
+        word = 0;
+        base = -32;
+        wnext = ncand > 0 ? __ldg(mask) : 0u;
+        mw = mask + 1;
+    }
+    __device__ __forceinline__ void get(int k, u64& H, int& p)
+    {
+        H = h1;
+        h1 = h2;
+        if (k + 2 < ncand)
+            h2 = VC_LOAD_STREAM(gp);
+        gp += stride;
+        if (k + ED_PFD < ncand)
+            VC_PREFETCH_L2(gpf);
+        gpf += stride;
+        while (word == 0u)
+        { // k < ncand: there is a set bit ahead, so the walk never leaves the bitmap (one word of slack is allocated)
+            word = wnext;
+            wnext = __ldg(mw++);
+            base += 32;
+        }
+        p = base + __ffs(word) - 1;
+        word &= word - 1;
+    }
+};
+
+// 1 / (8w): the spacing w of two neighbours on the stack is almost always a few positions, so the first RCP_SM
+// entries of the table sit in shared memory (one LDS, no dependence on what is left of L1 next to the rings);
+// larger spacings read the global table.
+#ifndef RCP_SM
+#define RCP_SM 128
+#endif
+struct RcpTable
+{
+    const double* sm;
+    const double* __restrict__ gl;
+    __device__ __forceinline__ double operator[](int w) const
+    {
+#if RCP_SM > 0
+        return w < RCP_SM ? sm[w] : __ldg(gl + w);
+#else
+        return __ldg(gl + w);
+#endif
+    }
+};
+#define RCP_SETUP(gl_ptr)                                                \
+    __shared__ double rcp_sm[RCP_SM > 0 ? RCP_SM : 1];                   \
+    for (int i = threadIdx.x; i < RCP_SM; i += XY_THREADS)               \
+        rcp_sm[i] = gl_ptr[i];                                           \
+    __syncthreads();                                                     \
+    const RcpTable rcp{rcp_sm, gl_ptr};
+
 // ---- passes X and Y ------------------------------------------------------------------------------------
-#define XY_THREADS 128
-#define XY_TW 16 // pass X: targets per transposed store burst (rows of XY_TW * 8 = 128 bytes)
+#ifndef XY_TW
+#define XY_TW 8 // pass X: targets per transposed store burst (rows of XY_TW * 8 = 64 bytes = two full sectors)
+#endif
 #ifndef XY_MINB
 #define XY_MINB 8 // resident blocks per SM the register allocation must allow
 #endif
@@ -212,11 +341,12 @@ struct StackRing
 // memory and written as rows of 128 bytes of G2c[plane][r][vx].
 __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
     k_pass_x(const u64* __restrict__ G1c, u64* __restrict__ G2c, uint4* __restrict__ spill, const int* __restrict__ row_ptr,
-             const int* __restrict__ live_row, const int* __restrict__ col_x, const int* __restrict__ meta, int pz, int ngroups,
-             int nx, size_t spill_stride, const double* __restrict__ rcp8w)
+             const int* __restrict__ live_row, const u32* __restrict__ colmask, int nw, const int* __restrict__ meta, int pz,
+             int ngroups, int nx, size_t spill_stride, const double* __restrict__ rcp8w)
 {
     __shared__ u64 tile[XY_THREADS / 32][32][XY_TW + 1];
-    __shared__ uint4 rings[SR_R * XY_THREADS];
+    __shared__ uint4 rings[SR_RX * XY_THREADS];
+    RCP_SETUP(rcp8w)
     const int nlive = meta[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = blockIdx.x * (XY_THREADS / 32) + warp;
@@ -226,63 +356,68 @@ __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
     const int cy = live_row[r], c0 = row_ptr[cy], nc = row_ptr[cy + 1] - c0;
     const int v = grp * 32 + lane; // plane of this lane inside the chunk
     const bool valid = v < pz;
-    StackRing stk;
-    stk.ring = rings + threadIdx.x;
-    stk.glob = spill + ((size_t)r * pz + (valid ? v : 0)) * spill_stride;
-    stk.nthr = XY_THREADS;
+    StackRing<SR_RX> stk;
+    stk.sbase = (unsigned)__cvta_generic_to_shared(rings + threadIdx.x);
+    stk.glob = spill + (size_t)w * 32 * spill_stride + lane; // the warp's block of 32 interleaved stacks
     stk.lo = 0;
+    CandStream src;
+    src.init(G1c + (size_t)c0 * pz + (valid ? v : 0), (long)pz, colmask + (size_t)cy * nw, valid ? nc : 0);
     const int rsub = lane / XY_TW, col = lane % XY_TW; // a store instruction covers 32 / XY_TW rows
     const int v0 = grp * 32;
-    vc_envelope_pruned(G1c + (size_t)c0 * pz + v, (long)pz, col_x + c0, valid ? nc : 0, nx, stk,
-                 [&](int t, u32 V, u32 id)
-                 {
-                     tile[warp][lane][t % XY_TW] = ((u64)V << 32) | id;
-                     if ((t % XY_TW) == 0)
-                     {
-                         __syncwarp();
-                         const bool colok = t + col < nx;
-                         u64* dst = G2c + ((size_t)(v0 + rsub) * nlive + r) * nx + t + col;
+    vc_envelope_pruned(src, valid ? nc : 0, nx, stk,
+                       [&](int t, u32 V, u32 id)
+                       {
+                           tile[warp][lane][t % XY_TW] = ((u64)V << 32) | id;
+                           if ((t % XY_TW) == 0)
+                           {
+                               __syncwarp();
+                               const bool colok = t + col < nx;
+                               u64* dst = G2c + ((size_t)(v0 + rsub) * nlive + r) * nx + t + col;
 #pragma unroll 4
-                         for (int rr = rsub; rr < 32; rr += 32 / XY_TW, dst += (size_t)(32 / XY_TW) * nlive * nx)
-                             if (colok && v0 + rr < pz)
-                                 *dst = tile[warp][rr][col];
-                         __syncwarp();
-                     }
-                 });
+                               for (int rr = rsub; rr < 32; rr += 32 / XY_TW, dst += (size_t)(32 / XY_TW) * nlive * nx)
+                                   if (colok && v0 + rr < pz)
+                                       *dst = tile[warp][rr][col];
+                               __syncwarp();
+                           }
+                       },
+                       rcp);
 }
 
 // pass Y: line = (plane, vx), lanes along vx; candidates = the live rows; writes id / 4d^2 coalesced.
 __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
     k_pass_y(const u64* __restrict__ G2c, int* __restrict__ id_out, u32* __restrict__ d2_out, uint4* __restrict__ spill,
-             const int* __restrict__ live_row, const int* __restrict__ meta, long nlines, int nx, int ny, size_t spill_stride,
+             const u32* __restrict__ row_mask, const int* __restrict__ meta, long nlines, int nx, int ny, size_t spill_stride,
              const double* __restrict__ rcp8w)
 {
-    __shared__ uint4 rings[SR_R * XY_THREADS];
+    __shared__ uint4 rings[SR_RY * XY_THREADS];
+    RCP_SETUP(rcp8w)
     const int nlive = meta[1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = g < nlines;
     const long plane = valid ? g / nx : 0;
     const int vx = valid ? (int)(g - plane * nx) : 0;
-    StackRing stk;
-    stk.ring = rings + threadIdx.x;
-    stk.glob = spill + (size_t)(valid ? g : 0) * spill_stride;
-    stk.nthr = XY_THREADS;
+    StackRing<SR_RY> stk;
+    stk.sbase = (unsigned)__cvta_generic_to_shared(rings + threadIdx.x);
+    stk.glob = spill + (size_t)(g - lane) * spill_stride + lane; // the warp's block of 32 interleaved stacks
     stk.lo = 0;
+    CandStream src;
+    src.init(G2c + (size_t)plane * nlive * nx + vx, (long)nx, row_mask, valid ? nlive : 0);
     const long last = (plane * ny + (ny - 1)) * (long)nx + vx;
     int* pid = id_out + last;
     u32* pd2 = d2_out + last;
-    vc_envelope_pruned(G2c + (size_t)plane * nlive * nx + vx, (long)nx, live_row, valid ? nlive : 0, ny, stk,
-                 [&](int t, u32 V, u32 id)
-                 { // targets arrive as ny-1 .. 0
-                     if (valid)
-                     {
-                         __stcs(pid, (int)id);
-                         __stcs(pd2, V);
-                     }
-                     pid -= nx;
-                     pd2 -= nx;
-                 },
-                 rcp8w);
+    vc_envelope_pruned(src, valid ? nlive : 0, ny, stk,
+                       [&](int t, u32 V, u32 id)
+                       { // targets arrive as ny-1 .. 0
+                           if (valid)
+                           {
+                               __stcs(pid, (int)id);
+                               __stcs(pd2, V);
+                           }
+                           pid -= nx;
+                           pd2 -= nx;
+                       },
+                       rcp);
 }
 
 __global__ void k_rcp_table(double* t, int n)
@@ -297,8 +432,9 @@ __global__ void k_rcp_table(double* t, int n)
 static size_t stack_region_entries(const vc_ctx* c, int planes)
 {
     const size_t CY = c->ny + 1;
-    const size_t lines = CY > (size_t)c->nx ? CY : (size_t)c->nx; // pass X: <= CY live rows, pass Y: nx lines per plane
-    return (size_t)planes * lines * ST_STRIDE(c);
+    const size_t lx = CY * (size_t)((planes + 31) / 32 * 32);                          // pass X: <= CY live rows x 32-plane groups
+    const size_t ly = ((size_t)planes * c->nx + XY_THREADS - 1) / XY_THREADS * XY_THREADS; // pass Y: whole blocks of lines
+    return (lx > ly ? lx : ly) * ST_STRIDE(c);
 }
 
 // compact column tables of the current site set (once per site set: st_finalize_sites clears edt_cols_ready)
@@ -319,8 +455,9 @@ static int edt_columns(vc_ctx* c)
     const size_t cap = (size_t)c->nsites < ncolcap ? (size_t)c->nsites : ncolcap;
     VC_CUDA(c, c->col_x.ensure((cap + 1) * 4));
     VC_CUDA(c, c->col_line.ensure((cap + 1) * 4));
+    VC_CUDA(c, c->row_mask.ensure((size_t)(((CY + 31) >> 5) + 2) * 4));
     VC_LAUNCH(c, "edt_columns", k_col_rows, 1, 1024, 0, c->colmask.as<u32>(), CY, nw, c->row_ptr.as<int>(), c->live_row.as<int>(),
-              c->edt_meta.as<int>());
+              c->row_mask.as<u32>(), c->edt_meta.as<int>());
     VC_LAUNCH(c, "edt_columns", k_col_fill, vc_blocks((size_t)CY * nw, 256), 256, 0, c->colmask.as<u32>(), c->row_ptr.as<int>(), CY,
               nw, c->col_x.as<int>(), c->col_line.as<int>());
     c->edt_cols_ready = true;
@@ -365,11 +502,12 @@ int edt_range(vc_ctx* c, int zb, int ze, int region, int region_planes)
         const int ngroups = (pz + 31) / 32;
         const size_t warps = (size_t)CY * ngroups; // warps of rows that are not live leave at once
         VC_LAUNCH(c, "edt_pass_x", k_pass_x, vc_blocks(warps, XY_THREADS / 32), XY_THREADS, 0, g1, g2, spill, c->row_ptr.as<int>(),
-                  c->live_row.as<int>(), c->col_x.as<int>(), meta, pz, ngroups, c->nx, ST_STRIDE(c), c->rcp8w.as<double>());
+                  c->live_row.as<int>(), c->colmask.as<u32>(), (CX + 31) >> 5, meta, pz, ngroups, c->nx, ST_STRIDE(c),
+                  c->rcp8w.as<double>());
     }
     const long nlines = (long)pz * c->nx;
     VC_LAUNCH(c, "edt_pass_y", k_pass_y, vc_blocks((size_t)nlines, XY_THREADS), XY_THREADS, 0, g2,
-              c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, spill, c->live_row.as<int>(), meta, nlines,
+              c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, spill, c->row_mask.as<u32>(), meta, nlines,
               c->nx, c->ny, ST_STRIDE(c), c->rcp8w.as<double>());
     return VC_OK;
 }
