@@ -114,9 +114,6 @@ extern "C"
     {
         const int CX = nx + 1, CY = ny + 1;
         const int nzs = z1 - z0;
-        std::vector<double> rcp(2050, 0.0);
-        for (int w = 1; w < 2050; ++w)
-            rcp[w] = 1.0 / (8.0 * w);
         // z-line lists per column, then the compact list of columns that hold sites, row by row (cy major, cx ascending)
         std::vector<std::vector<vc_u64>> lines((size_t)CX * CY);
         for (int64_t s = 0; s < ns; ++s)
@@ -160,7 +157,7 @@ extern "C"
                 vc_pstack_array stk{stkv.data()};
                 vc_psource_array src{&G1[(size_t)c0 * nzs + vz], (long)nzs, &colx[c0]};
                 vc_envelope_pruned(src, nc, nx, stk,
-                                   [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; }, rcp.data());
+                                   [&](int t, uint32_t V, uint32_t id) { row[t] = ((vc_u64)V << 32) | id; });
                 st[0]++, st[1] += nc, st[2] += stk.npop, st[3] = std::max<int64_t>(st[3], stk.maxdepth + 1);
                 if (depth_hist)
                     depth_hist[std::min(stk.maxdepth + 1, 63)]++;
@@ -177,8 +174,7 @@ extern "C"
                                        size_t o = (size_t)vx + (size_t)nx * ((size_t)t + (size_t)ny * vz);
                                        id_out[o] = (int32_t)id;
                                        d2x4_out[o] = V;
-                                   },
-                                   rcp.data());
+                                   });
                 st[4]++, st[5] += nlive, st[6] += stk.npop, st[7] = std::max<int64_t>(st[7], stk.maxdepth + 1);
                 if (depth_hist)
                     depth_hist[64 + std::min(stk.maxdepth + 1, 63)]++;
@@ -191,9 +187,6 @@ extern "C"
     // only ever see live candidates
     void hh_envelope_pruned(const vc_u64* in, int ncand, int ntgt, vc_u64* out)
     {
-        std::vector<double> rcp(2050, 0.0);
-        for (int w = 1; w < 2050; ++w)
-            rcp[w] = 1.0 / (8.0 * w);
         std::vector<vc_u64> h;
         std::vector<int> pos;
         for (int j = 0; j < ncand; ++j)
@@ -203,35 +196,34 @@ extern "C"
         vc_pstack_array stk{stkv.data()};
         vc_psource_array src{h.data(), 1L, pos.data()};
         vc_envelope_pruned(src, (int)h.size(), ntgt, stk,
-                           [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; }, rcp.data());
+                           [&](int t, uint32_t V, uint32_t id) { out[t] = ((vc_u64)V << 32) | id; });
     }
 
-    // vc_sep against plain integer floor division: returns the number of mismatches over all divisors w in [1, 2048]
-    // and the numerators around every multiple of 8w plus the extremes
+    // vc_sep against plain integer floor division: the number of mismatches over all spacings w in [1, 2048], line
+    // lengths ntgt and the numerators around every multiple of 8w in the range the scan can produce (N > 0)
     int64_t hh_sep_sweep(void)
     {
-        std::vector<double> rcp(2050, 0.0);
-        for (int w = 1; w < 2050; ++w)
-            rcp[w] = 1.0 / (8.0 * w);
         int64_t bad = 0;
-        auto fl = [](long long a, long long b) { long long q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+        const int ntgts[] = {1, 2, 7, 64, 511, 512, 1024, 2047, 2048};
         for (int w = 1; w <= 2048; ++w)
         {
             const long long d = 8LL * w;
-            auto check = [&](long long N)
-            { // N = dg + c - 1 + 4w  ->  dg = N - c + 1 - 4w with c = 0
-                if (N < -(1LL << 28) || N > (1LL << 28))
-                    return;
-                int got = vc_sep((int)(N + 1 - 4 * w), 0, w, rcp.data());
-                if (got != (int)fl(N, d))
-                    ++bad;
-            };
-            for (long long k = -(1LL << 27) / d - 1; k <= (1LL << 27) / d + 1; k += std::max<long long>(1, ((1LL << 27) / d) / 3000))
-                for (int e = -2; e <= 2; ++e)
-                    check(k * d + e);
-            for (long long N = -40000; N <= 40000; ++N)
-                check(N);
-            check((1LL << 28) - 1), check(-(1LL << 28) + 1);
+            for (int ntgt : ntgts)
+            {
+                auto check = [&](long long N)
+                { // N = dg + c - 1 + 4w  ->  dg = N + 1 - 4w with c = 0
+                    if (N <= 0 || N > (1LL << 28))
+                        return;
+                    const int got = vc_sep((int)(N + 1 - 4 * w), 0, w, ntgt);
+                    const long long want = N / d;
+                    if (want >= ntgt ? got < ntgt : got != (int)want)
+                        ++bad;
+                };
+                for (long long k = 0; k <= ntgt + 2; k += (ntgt > 600 && w > 64) ? 7 : 1)
+                    for (int e = -2; e <= 9; ++e)
+                        check(k * d + e);
+                check((1LL << 28) - 1), check((1LL << 27) + 12345);
+            }
         }
         return bad;
     }

@@ -4,14 +4,13 @@ sys.path.insert(0, ".")
 from voxel_ma_b200 import build as vb
 VARIANTS = {
     "base": [],
-    "ringy16": ["-DSR_RY=16"],
+    "d2": ["-DED_DEPTH=2"],
+    "d3": ["-DED_DEPTH=3"],
+    "d6": ["-DED_DEPTH=6"],
+    "d4_pf0": ["-DED_PFD=0"],
+    "d4_pf24": ["-DED_PFD=24"],
+    "d6_pf0": ["-DED_DEPTH=6", "-DED_PFD=0"],
     "wi_nospill": ["-DWHATIF_NOSPILL"],
-    "wi_norefill": ["-DWHATIF_NOREFILL"],
-    "wi_nospill_norefill": ["-DWHATIF_NOSPILL", "-DWHATIF_NOREFILL"],
-    "wi_nodiv": ["-DWHATIF_NODIV"],
-    "wi_noback": ["-DWHATIF_NOBACK"],
-    "wi_all": ["-DWHATIF_NOSPILL", "-DWHATIF_NOREFILL", "-DWHATIF_NODIV"],
-    "minb12": ["-DXY_MINB=12"],
 }
 names = sys.argv[1:] or list(VARIANTS)
 for n in names:

@@ -250,21 +250,32 @@ VC_HD void vc_envelope_line(const vc_u64* __restrict__ in, long stride, int ncan
 // Distance ties never need a second look (the id is part of the order), and the stack depth is bounded by the
 // number of distinct winners of the line instead of the number of parabolas touching the real-valued envelope.
 //
-// The one division is done in double: |N| < 2^28, divisor 8w <= 2^14; the true quotient of (N + 0.5) / (8w) is
-// at least 2^-15 away from every integer and the product with the rounded reciprocal is off by < 2^-24, so the
-// floor is exact (tests/test_host_core.py sweeps every divisor).  rcp8w[w] = 1.0 / (8 w), w in [1, 2048].
-template <class Rcp>
-VC_HD int vc_sep(int dg, int c, int w, const Rcp& rcp8w)
+// The one division needs no division instruction and no table: a candidate whose start would lie beyond the last
+// target is recognised by a multiplication (N >= ntgt * 8w) and dropped; for the others N > 0, the quotient is
+// below ntgt <= 2048 and M = N >> 3 < 2^22 is exact in float, so trunc(float(M) * rcp(w)) is off by at most one
+// (relative error of the reciprocal and of the product <= 2^-22, quotient < 2^11) and one remainder check makes
+// it exact -- with the approximate reciprocal of the device (rcp.approx, 1 ulp) as with the host's 1.0f / w, so
+// both produce the same integers (tests/test_host_core.py sweeps every divisor).
+// Returns the start, or a value >= ntgt when the candidate never wins inside [0, ntgt).
+VC_HD int vc_sep(int dg, int c, int w, int ntgt)
 {
-    const int N = dg + c - 1 + 4 * w;
+    const int N = dg + c - 1 + 4 * w; // > 0: the caller's top survived at its own start, so the new start is >= 1
+    if (N >= ntgt * 8 * w)
+        return ntgt;
+    const int M = N >> 3;
 #if defined(__CUDA_ARCH__) && defined(WHATIF_NODIV) // timing experiment only: wrong results
-    return N >> 3;
-#elif defined(__CUDA_ARCH__)
-    return __double2int_rd(((double)N + 0.5) * rcp8w[w]);
+    return M;
 #else
-    double qd = ((double)N + 0.5) * rcp8w[w];
-    int q = (int)qd;
-    return (double)q > qd ? q - 1 : q; // floor
+#if defined(__CUDA_ARCH__)
+    float rw;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rw) : "f"((float)w));
+    int q = __float2int_rz(__fmul_rn((float)M, rw));
+#else
+    int q = (int)((float)M * (1.0f / (float)w));
+#endif
+    const int r = M - q * w;
+    q += (r >= w ? 1 : 0) - (r < 0 ? 1 : 0);
+    return q;
 #endif
 }
 
@@ -332,8 +343,8 @@ struct vc_psource_array
 #endif
 
 // One line.  emit(t, V, id) is called for t = ntgt-1 .. 0 (all-ones when the line has no candidate).
-template <class Source, class Stack, class Emit, class Rcp>
-VC_HD void vc_envelope_pruned(Source& src, int ncand, int ntgt, Stack& stk, Emit emit, const Rcp& rcp8w)
+template <class Source, class Stack, class Emit>
+VC_HD void vc_envelope_pruned(Source& src, int ncand, int ntgt, Stack& stk, Emit emit)
 {
     int q = -1; // depth of the top (registers); depths 0 .. q-1 are in stk
     int gt = 0, pt = 0, st = 0, at = 0; // at = 4 (2 st + 1)
@@ -366,7 +377,7 @@ VC_HD void vc_envelope_pruned(Source& src, int ncand, int ntgt, Stack& stk, Emit
         int s = 0;
         if (q >= 0)
         {
-            s = vc_sep(g - gt, id < idt ? 0 : 1, j - pt, rcp8w);
+            s = vc_sep(g - gt, id < idt ? 0 : 1, j - pt, ntgt);
             if (s >= ntgt)
                 continue; // never the winner inside the line
             vc_ent e;

@@ -251,18 +251,21 @@ struct StackRing
 };
 
 // ---- candidate stream ----------------------------------------------------------------------------------
-// Words: two candidates ahead in registers, ED_PFD candidates ahead in L2 (prefetch.global.L2: no register, no
+// Words: ED_DEPTH candidates ahead in registers, ED_PFD candidates ahead in L2 (prefetch.global.L2: no register, no
 // shared memory -- the shared-memory pipe is what bounds these kernels, so the fetch stays out of it).
 // Positions: the candidates of a warp are the set bits of a bitmap that is the same for every lane (pass X: the
 // row's columns, `colmask`; pass Y: the live rows, `row_mask`), walked with ffs -- no load per candidate at all.
 #ifndef ED_PFD
-#define ED_PFD 24
+#define ED_PFD 8 // L2 prefetch distance in candidates (0: none)
+#endif
+#ifndef ED_DEPTH
+#define ED_DEPTH 4 // candidates in flight in registers
 #endif
 struct CandStream
 {
     const u64 *gp, *gpf; // word of the next candidate to load / to prefetch
     long stride;
-    u64 h1, h2;
+    u64 h[ED_DEPTH];
     const u32* mw; // next bitmap word
     u32 word, wnext;
     int base, ncand;
@@ -270,12 +273,14 @@ struct CandStream
     {
         stride = stride_;
         ncand = ncand_;
-        h1 = ncand > 0 ? VC_LOAD_STREAM(src) : 0ull;
-        h2 = ncand > 1 ? VC_LOAD_STREAM(src + stride) : 0ull;
-        gp = src + 2 * stride;
+        gp = src;
+#pragma unroll
+        for (int i = 0; i < ED_DEPTH; ++i, gp += stride)
+            h[i] = i < ncand ? VC_LOAD_STREAM(gp) : 0ull;
         gpf = gp;
-        for (int i = 2; i < ED_PFD && i < ncand; ++i, gpf += stride)
-            VC_PREFETCH_L2(gpf);
+        if (ED_PFD > 0)
+            for (int i = ED_DEPTH; i < ED_PFD && i < ncand; ++i, gpf += stride)
+                VC_PREFETCH_L2(gpf);
         word = 0;
         base = -32;
         wnext = ncand > 0 ? __ldg(mask) : 0u;
@@ -283,14 +288,19 @@ struct CandStream
     }
     __device__ __forceinline__ void get(int k, u64& H, int& p)
     {
-        H = h1;
-        h1 = h2;
-        if (k + 2 < ncand)
-            h2 = VC_LOAD_STREAM(gp);
+        H = h[0];
+#pragma unroll
+        for (int i = 0; i + 1 < ED_DEPTH; ++i)
+            h[i] = h[i + 1];
+        if (k + ED_DEPTH < ncand)
+            h[ED_DEPTH - 1] = VC_LOAD_STREAM(gp);
         gp += stride;
-        if (k + ED_PFD < ncand)
-            VC_PREFETCH_L2(gpf);
-        gpf += stride;
+        if (ED_PFD > 0)
+        {
+            if (k + ED_PFD < ncand)
+                VC_PREFETCH_L2(gpf);
+            gpf += stride;
+        }
         while (word == 0u)
         { // k < ncand: there is a set bit ahead, so the walk never leaves the bitmap (one word of slack is allocated)
             word = wnext;
@@ -301,32 +311,6 @@ struct CandStream
         word &= word - 1;
     }
 };
-
-// 1 / (8w): the spacing w of two neighbours on the stack is almost always a few positions, so the first RCP_SM
-// entries of the table sit in shared memory (one LDS, no dependence on what is left of L1 next to the rings);
-// larger spacings read the global table.
-#ifndef RCP_SM
-#define RCP_SM 128
-#endif
-struct RcpTable
-{
-    const double* sm;
-    const double* __restrict__ gl;
-    __device__ __forceinline__ double operator[](int w) const
-    {
-#if RCP_SM > 0
-        return w < RCP_SM ? sm[w] : __ldg(gl + w);
-#else
-        return __ldg(gl + w);
-#endif
-    }
-};
-#define RCP_SETUP(gl_ptr)                                                \
-    __shared__ double rcp_sm[RCP_SM > 0 ? RCP_SM : 1];                   \
-    for (int i = threadIdx.x; i < RCP_SM; i += XY_THREADS)               \
-        rcp_sm[i] = gl_ptr[i];                                           \
-    __syncthreads();                                                     \
-    const RcpTable rcp{rcp_sm, gl_ptr};
 
 // ---- passes X and Y ------------------------------------------------------------------------------------
 #ifndef XY_TW
@@ -342,11 +326,10 @@ struct RcpTable
 __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
     k_pass_x(const u64* __restrict__ G1c, u64* __restrict__ G2c, uint4* __restrict__ spill, const int* __restrict__ row_ptr,
              const int* __restrict__ live_row, const u32* __restrict__ colmask, int nw, const int* __restrict__ meta, int pz,
-             int ngroups, int nx, size_t spill_stride, const double* __restrict__ rcp8w)
+             int ngroups, int nx, size_t spill_stride)
 {
     __shared__ u64 tile[XY_THREADS / 32][32][XY_TW + 1];
     __shared__ uint4 rings[SR_RX * XY_THREADS];
-    RCP_SETUP(rcp8w)
     const int nlive = meta[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = blockIdx.x * (XY_THREADS / 32) + warp;
@@ -379,18 +362,15 @@ __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
                                        *dst = tile[warp][rr][col];
                                __syncwarp();
                            }
-                       },
-                       rcp);
+                       });
 }
 
 // pass Y: line = (plane, vx), lanes along vx; candidates = the live rows; writes id / 4d^2 coalesced.
 __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
     k_pass_y(const u64* __restrict__ G2c, int* __restrict__ id_out, u32* __restrict__ d2_out, uint4* __restrict__ spill,
-             const u32* __restrict__ row_mask, const int* __restrict__ meta, long nlines, int nx, int ny, size_t spill_stride,
-             const double* __restrict__ rcp8w)
+             const u32* __restrict__ row_mask, const int* __restrict__ meta, long nlines, int nx, int ny, size_t spill_stride)
 {
     __shared__ uint4 rings[SR_RY * XY_THREADS];
-    RCP_SETUP(rcp8w)
     const int nlive = meta[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,15 +396,7 @@ __global__ void __launch_bounds__(XY_THREADS, XY_MINB)
                            }
                            pid -= nx;
                            pd2 -= nx;
-                       },
-                       rcp);
-}
-
-__global__ void k_rcp_table(double* t, int n)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < n)
-        t[w] = w ? 1.0 / (8.0 * (double)w) : 0.0;
+                       });
 }
 
 // scratch for the envelope stacks: one region per z chunk of the pipeline (chunks run concurrently), a region
@@ -442,11 +414,6 @@ static int edt_columns(vc_ctx* c)
 {
     const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
     const size_t ncolcap = (size_t)CX * CY;
-    if (!c->rcp8w.p)
-    {
-        VC_CUDA(c, c->rcp8w.ensure(2052 * sizeof(double)));
-        VC_LAUNCH(c, "edt_rcp_table", k_rcp_table, vc_blocks(2052, 256), 256, 0, c->rcp8w.as<double>(), 2052);
-    }
     if (c->edt_cols_ready)
         return VC_OK;
     VC_CUDA(c, c->row_ptr.ensure((size_t)(CY + 2) * 4));
@@ -502,13 +469,12 @@ int edt_range(vc_ctx* c, int zb, int ze, int region, int region_planes)
         const int ngroups = (pz + 31) / 32;
         const size_t warps = (size_t)CY * ngroups; // warps of rows that are not live leave at once
         VC_LAUNCH(c, "edt_pass_x", k_pass_x, vc_blocks(warps, XY_THREADS / 32), XY_THREADS, 0, g1, g2, spill, c->row_ptr.as<int>(),
-                  c->live_row.as<int>(), c->colmask.as<u32>(), (CX + 31) >> 5, meta, pz, ngroups, c->nx, ST_STRIDE(c),
-                  c->rcp8w.as<double>());
+                  c->live_row.as<int>(), c->colmask.as<u32>(), (CX + 31) >> 5, meta, pz, ngroups, c->nx, ST_STRIDE(c));
     }
     const long nlines = (long)pz * c->nx;
     VC_LAUNCH(c, "edt_pass_y", k_pass_y, vc_blocks((size_t)nlines, XY_THREADS), XY_THREADS, 0, g2,
               c->id.as<int>() + off * c->nx * c->ny, c->d2.as<u32>() + off * c->nx * c->ny, spill, c->row_mask.as<u32>(), meta, nlines,
-              c->nx, c->ny, ST_STRIDE(c), c->rcp8w.as<double>());
+              c->nx, c->ny, ST_STRIDE(c));
     return VC_OK;
 }
 

@@ -99,8 +99,8 @@ struct vc_ctx
     DevBuf g1, g2, id, d2, edge3, face3, cube, radius;
     DevBuf stk; // spill space of the envelope stacks of the transform passes (16-byte entries per line and depth)
     // compact columns of the site set (vc_edt.cu): row_ptr[cy] = first column of row cy, col_x / col_line per column,
-    // live_row = rows that hold columns, edt_meta = {#columns, #live rows}; rcp8w[w] = 1 / (8w) for vc_sep
-    DevBuf row_ptr, live_row, row_mask, col_x, col_line, edt_meta, rcp8w;
+    // live_row = rows that hold columns (row_mask: the same as a bitmap), edt_meta = {#columns, #live rows}
+    DevBuf row_ptr, live_row, row_mask, col_x, col_line, edt_meta;
     bool edt_cols_ready = false;
     std::vector<cudaEvent_t> ev_chunk; // "transform of z chunk k done" (the next chunk's measures wait for it)
     // sort scratch
