@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric: grid vertices/s through classify + closest-site + measures.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--grid NX,NY,NZ]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--grid NX,NY,NZ] [--weak]
 
 One "step" = one pass of the hot path (classify -> boundary samples -> closest site per grid vertex
 -> cell measures) over the synthetic volume, which is already resident in HBM when the timed region
-starts.  N=1 runs BASELINE config[2] (twist512, the configuration the metric is quoted on); N>1
-keeps 512^3 vertices per GPU (weak scaling): 512x512x1024, 512x1024x1024, 1024^3 (= config[3],
-assembly1024) cut into z-slabs, one process per GPU, the site records all-gathered over NCCL.
+starts.  Workload, by default the SAME for every N so that the 1/2/4/8-GPU numbers form one STRONG-scaling
+curve: BASELINE configs[3], assembly1024 (1024^3 vertices, 2.7e6 boundary samples; 75 GB resident on one
+B200), cut into N z-slabs, one process per GPU, the site records exchanged over peer memory (NVLink).  At
+N=1 the line also carries "at_512": the same measurements on configs[2], twist512 -- the 512^3
+configuration the metric's single-GPU target is quoted on.  `--weak` keeps 512^3 vertices per GPU instead
+(512^3 / 512x512x1024 / 512x1024x1024 / 1024^3), `--workload twist512` etc. picks one explicitly.
 Rank 0 prints ONE JSON line.  `--impl reference` times the reference's own CPU operators instead
 (oracle/_ref, bounded sample) and prints the same line with "impl": "reference".
 """
@@ -31,22 +34,28 @@ UNIT = "vertices/s"
 # algorithmic bytes per grid vertex, SURVEY.md section 8(d) (stated again in DESIGN.md)
 BYTES_CLASSIFY, BYTES_CLOSEST, BYTES_MEASURES = 5, 8, 32
 BYTES_PIPELINE = BYTES_CLASSIFY + BYTES_CLOSEST + BYTES_MEASURES  # 45
-# bytes one launch of a kernel has to move by its own contract, per unit it processes
+STAGE_OF = {"classify_f32": "classify", "classify_i8": "classify", "edt_pass_z": "closest", "edt_pass_x": "closest",
+            "edt_pass_y": "closest", "cell_measures": "measures"}
+STAGE_BYTES = {"classify": BYTES_CLASSIFY, "closest": BYTES_CLOSEST, "measures": BYTES_MEASURES}
 WEAK_GRIDS = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (512, 1024, 1024), 8: (1024, 1024, 1024)}
+STRONG = ("assembly", (1024, 1024, 1024))  # BASELINE configs[3]
+AT_512 = ("twist", (512, 512, 512))        # BASELINE configs[2]
 
 
 def workload_for(n_gpus, args):
+    """-> (family, grid, scaling)"""
     if args.grid:
         g = tuple(int(v) for v in args.grid.split(","))
-        name = args.workload or "assembly"
-        return name, g
+        return args.workload or "assembly", g, "strong"
     if args.workload:
         fam = args.workload.rstrip("0123456789")
         side = int(args.workload[len(fam):] or 512)
-        return fam, (side, side, side)
-    if n_gpus == 1:
-        return "twist", WEAK_GRIDS[1]
-    return "assembly", WEAK_GRIDS.get(n_gpus, (512, 512, 512 * n_gpus))
+        return fam, (side, side, side), "strong"
+    if args.weak:
+        if n_gpus == 1:
+            return "twist", WEAK_GRIDS[1], "weak"
+        return "assembly", WEAK_GRIDS.get(n_gpus, (512, 512, 512 * n_gpus)), "weak"
+    return STRONG[0], STRONG[1], "strong"
 
 
 def make_planes(fam, grid, z0, z1):
@@ -136,14 +145,35 @@ def _sites_worker(block):
     return ob.ref().ref_last_seconds()
 
 
-def cpu_reference_rate(fam, grid, budget_s=20.0, cores=None):
-    """vertices/s of the reference's CPU operators for this path, all host cores, bounded sample.
+_SITE_CACHE = {}
 
-    classify + boundary samples: Surfacer::extractBoundaryVts (which calls voxTaggedAsInside 7x per
-    voxel) on one sub-block per core; closest: ANNkd_tree build + annkSearch(k=1,eps=0) over the FULL
-    site set, one forked process per core (ANN keeps search state in globals), a random sample of grid
-    vertices as queries; measures: the lambdaForFace dictionary (C port) on a slab.  The three
-    per-vertex costs add up exactly as they would in a whole-grid run."""
+
+def full_site_set(fam, grid):
+    """The boundary samples of the WHOLE grid, in the reference's order (oracle/oracle.c port of extractBoundaryVts,
+    classified slab by slab); not timed -- the ANN leg needs the true site set at every size.  Cached per workload."""
+    from oracle import bindings as ob
+    key = (fam, grid)
+    if key not in _SITE_CACHE:
+        nx, ny, nz = grid
+        inside = np.empty((nz, ny, nx), np.uint8)
+        for z in range(0, nz, 128):
+            inside[z:z + 128] = ob.classify_grid(make_planes(fam, grid, z, min(z + 128, nz)))
+        _SITE_CACHE[key] = ob.extract_sites(inside)
+    return _SITE_CACHE[key]
+
+
+def cpu_reference_rate(fam, grid, budget_s=20.0, cores=None):
+    """vertices/s of the reference's CPU operators for this path, all host cores, on a BOUNDED SAMPLE of the workload;
+    the whole-grid figure is an extrapolation (the per-vertex costs of the three stages are measured on their samples
+    and summed, exactly as they would add up in a whole-grid run) and is labelled as such.
+
+    A  classify + boundary samples: the reference's Surfacer::extractBoundaryVts (it calls voxTaggedAsInside 7x per
+       voxel) on one sub-block per core, through oracle/_ref/libvoxref.so;
+    B  closest: the reference's ANNkd_tree build + annkSearch(k=1, eps=0) over the FULL site set of the grid, one forked
+       process per core (ANN keeps search state in globals), uniformly random grid vertices as queries;
+    C  measures: the lambdaForFace dictionary -- a PORT (oracle/oracle.c, OpenMP): the reference evaluates lambdaForFace
+       on a Voronoi complex, the dense iteration space is the builder's; ids are synthetic but
+       distinct across neighbours so that every lambda is really evaluated."""
     import multiprocessing as mp
 
     from oracle import bindings as ob
@@ -151,24 +181,13 @@ def cpu_reference_rate(fam, grid, budget_s=20.0, cores=None):
     cores = cores or os.cpu_count() or 1
     nx, ny, nz = grid
     nvert = nx * ny * nz
+    t_total0 = time.perf_counter()
+    sites = full_site_set(fam, grid)
+    nsites = len(sites)
     # a slab through the middle of the object, thick enough to hold the sub-blocks
     zs = min(nz, 64)
-    zmid = nz // 2
-    slab0 = max(0, zmid - zs // 2)
+    slab0 = max(0, nz // 2 - zs // 2)
     planes = make_planes(fam, grid, slab0, slab0 + zs)
-    t_total0 = time.perf_counter()
-    # full site set (not timed: obtained with the C port; the ANN leg needs the true sites)
-    vol_full_sites = None
-    if nvert <= 512 ** 3:
-        full = make_planes(fam, grid, 0, nz)
-        inside_full = ob.classify_grid(full)
-        vol_full_sites = ob.extract_sites(inside_full)
-        del full
-    else:  # very large grids: sites of the sampled slab's neighbourhood only (stated in `sample`)
-        inside_full = ob.classify_grid(planes)
-        vol_full_sites = ob.extract_sites(inside_full)
-        vol_full_sites[:, 2] += slab0
-    nsites = len(vol_full_sites)
     ctx = mp.get_context("fork")
     # --- stage A: site extraction rate (voxels/s), one sub-block per core
     bs = min(ny, 128)
@@ -186,12 +205,14 @@ def cpu_reference_rate(fam, grid, budget_s=20.0, cores=None):
         for b in blocks:
             ob.extract_sites(ob.classify_grid(b))
         wall_a = (time.perf_counter() - t0) / cores
-    rate_a = sum(b.size for b in blocks) / max(wall_a, 1e-9)
+    nvox_a = sum(b.size for b in blocks)
+    rate_a = nvox_a / max(wall_a, 1e-9)
     # --- stage B: ANN 1-NN per grid vertex; size the sample from a short probe
     rng = np.random.default_rng(7)
+
     def queries(m):
         return np.stack([rng.integers(0, nx, m), rng.integers(0, ny, m), rng.integers(0, nz, m)], -1).astype(np.float64)
-    s64 = vol_full_sites.astype(np.float64)
+    s64 = sites.astype(np.float64)
     if kind == "reference" and nsites > 0:
         probe = 4000
         t_probe = _ann_worker((s64, queries(probe)))
@@ -202,50 +223,94 @@ def cpu_reference_rate(fam, grid, budget_s=20.0, cores=None):
         rate_b = cores * m_per_core / max(max(secs), 1e-9)
         nq = cores * m_per_core
     else:
-        m = 2000
+        nq = 2000
         t0 = time.perf_counter()
-        ob.closest_points(s64, queries(m)) if nsites else None
-        rate_b = m / max(time.perf_counter() - t0, 1e-9)
-        nq = m
+        ob.closest_points(s64, queries(nq)) if nsites else None
+        rate_b = nq / max(time.perf_counter() - t0, 1e-9)
     # --- stage C: measures on the slab (C port of the dictionary; OpenMP over the cores)
     ins = ob.classify_grid(planes)
-    ids = np.zeros(planes.shape, np.int32)
+    ids = ((np.arange(planes.size, dtype=np.int64) * 7919) % max(nsites, 1)).astype(np.int32).reshape(planes.shape)
     t0 = time.perf_counter()
     if nsites:
-        ob.cell_measures_grid(vol_full_sites, ids, ins, nx, ny, planes.shape[0], 0, planes.shape[0] - 1)
-    rate_c = planes[:-1].size / max(time.perf_counter() - t0, 1e-9)
+        ob.cell_measures_grid(sites, ids, ins, nx, ny, planes.shape[0], 0, planes.shape[0] - 1)
+    nv_c = planes[:-1].size
+    rate_c = nv_c / max(time.perf_counter() - t0, 1e-9)
     value = 1.0 / (1.0 / rate_a + 1.0 / rate_b + 1.0 / rate_c)
-    sample = (f"{fam} {nx}x{ny}x{nz}, {nsites} sites; extractBoundaryVts on {cores} sub-blocks of {zs}x{bs}x{bs} voxels "
-              f"({rate_a:.3g} voxels/s); ANN kd-tree build + {nq} annkSearch(k=1,eps=0) queries at random grid vertices over "
-              f"the full site set, one forked process per core ({rate_b:.3g} q/s); lambda dictionary on {planes.shape[0]-1} "
-              f"planes ({rate_c:.3g} v/s); per-vertex costs summed; {time.perf_counter()-t_total0:.1f}s of wall")
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    sample = (f"{fam} {nx}x{ny}x{nz}, {nsites} sites (the full site set); A: reference extractBoundaryVts on {cores} sub-blocks of "
+              f"{zs}x{bs}x{bs} voxels ({rate_a:.3g} voxels/s); B: reference ANN kd-tree build + {nq} annkSearch(k=1,eps=0) queries at "
+              f"random grid vertices, one forked process per core ({rate_b:.3g} q/s); C: lambda dictionary PORT on {planes.shape[0]-1} "
+              f"planes ({rate_c:.3g} v/s); per-vertex costs summed and extrapolated to the whole grid; "
+              f"{time.perf_counter()-t_total0:.1f}s of wall")
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "extrapolated": True,
+            "sampled_fraction": {"A_extract": nvox_a / nvert, "B_closest": nq / nvert, "C_measures": nv_c / nvert},
+            "stage_kinds": {"A_extract": kind, "B_closest": kind, "C_measures": "port"}}
+
+
+def cpu_reference_full(fam="torus", n=256, cores=None):
+    """A MEASURED (not extrapolated) CPU run of the whole path at BASELINE configs[1], torus256: the reference's
+    extractBoundaryVts over the whole volume (one thread: it is not parallel), the reference's ANN kd-tree at EVERY
+    grid vertex (forked workers on all cores), the lambda dictionary port on the whole grid.  ~10 s on 16 cores."""
+    from oracle import bindings as ob
+    from voxel_ma_b200 import synth
+    cores = cores or os.cpu_count() or 1
+    vol = synth.make(fam, n)
+    nz, ny, nx = vol.shape
+    t0 = time.perf_counter()
+    if ob.have_ref():
+        sites = ob.ref_extract_sites(vol)
+        t_a = ob.ref().ref_last_seconds()
+        kind = "reference"
+    else:
+        sites = ob.extract_sites(ob.classify_grid(vol))
+        t_a = time.perf_counter() - t0
+        kind = "port"
+    t1 = time.perf_counter()
+    if ob.have_ref():
+        ids, _, _ = ob.ref_ann_grid(sites, nx, ny, 0, nz, workers=cores)
+    else:
+        ids, _ = ob.closest_grid(sites, nx, ny, nz)
+    t_b = time.perf_counter() - t1
+    ins = ob.classify_grid(vol)
+    t2 = time.perf_counter()
+    ob.cell_measures_grid(sites, np.ascontiguousarray(ids), ins, nx, ny, nz)
+    t_c = time.perf_counter() - t2
+    tot = t_a + t_b + t_c
+    return {"workload": f"{fam}{n}", "vertices": nx * ny * nz, "sites": int(len(sites)), "cores": cores, "kind": kind,
+            "seconds": {"A_extract_1thread": t_a, "B_ann_every_vertex": t_b, "C_measures_port": t_c, "total": tot},
+            "value": nx * ny * nz / tot, "unit": UNIT, "extrapolated": False}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fam, grid = workload_for(args.gpus, args)
+    fam, grid, scaling = workload_for(args.gpus, args)
     vals = []
-    for _ in range(max(args.warmup, 0)):
-        pass  # the CPU path has no warm-up state worth the minutes it would take
     t0 = time.perf_counter()
     cb = None
-    for _ in range(max(1, min(args.steps, 3))):
-        with quiet_stdout():
+    with quiet_stdout():
+        full_site_set(fam, grid)  # untimed set-up, shared by the repeats
+        for _ in range(max(1, min(args.steps, 3))):  # each "step" = one bounded sample; the CPU path has no warm-up state
             cb = cpu_reference_rate(fam, grid, budget_s=12.0)
-        vals.append(cb["value"])
+            vals.append(cb["value"])
+        measured = None
+        try:
+            measured = cpu_reference_full()
+        except Exception as ex:  # the second point must not cost the first
+            measured = {"error": repr(ex)}
     v = float(np.median(vals))
     cb["value"] = v
     nvert = grid[0] * grid[1] * grid[2]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": nvert / v * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{fam}{grid[0]}x{grid[1]}x{grid[2]}", "note": "reference CPU operators (Surfacer + ANN kd-tree + "
-                   "lambdaForFace) on a bounded sample; ms_per_step is the whole-grid extrapolation"},
+        "warmup": args.warmup, "ms_per_step": nvert / v * 1e3, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": True,
+        "config": {"workload": f"{fam}{grid[0]}x{grid[1]}x{grid[2]}", "note": "reference CPU operators (Surfacer + ANN kd-tree; "
+                   "lambda dictionary port) on a bounded sample of the workload; value and ms_per_step are the whole-grid "
+                   "EXTRAPOLATION of the sampled per-vertex costs (cpu_baseline.sampled_fraction); cpu_reference_measured is a full, "
+                   "un-extrapolated run of the same three stages at torus256"},
         "cpu_baseline": cb,
+        "cpu_reference_measured": measured,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -253,35 +318,49 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def bind_to_gpu_numa(local):
+    """Pin this rank's threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU hangs off:
+    with 8 ranks all left on node 0 every upload of the other socket's GPUs crosses the inter-socket link.
+    Returns a short description for the JSON line; never fails the run."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"gpu": bdf, "numa_node": node, "bound": bool(allowed), "cpus": len(allowed)}
+    except Exception as ex:
+        return {"bound": False, "why": repr(ex)[:120]}
+
+
+def load_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one whole-slab launch of `kernel`, from the committed ncu capture"""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for entry in tj["captures"]:
+            if entry["workload"] == workload and kernel in entry["kernels"]:
+                k = entry["kernels"][kernel]
+                return (k["dram_read_gb"] + k["dram_write_gb"]) * 1e9, entry["source"], k.get("sm_throughput_pct")
+    except Exception:
+        pass
+    return None, None, None
+
+
+def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
+    """One workload on this process group.  Returns the JSON line (rank 0) or None.  sub=True: the condensed record of
+    the secondary N=1 workload ("at_512"): value, e2e and rooflines only."""
     import torch
 
     from voxel_ma_b200 import api, slabs
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    dist = None
-    torch.cuda.set_device(local)
-    # stdout must carry ONE line (rank 0's JSON): anything a library prints there meanwhile (NCCL's version banner
-    # under NCCL_DEBUG=VERSION, for one) is sent to stderr until the line is ready
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-
-    def emit(obj):
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(json.dumps(obj), flush=True)
-        os.dup2(2, 1)
-
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    fam, grid = workload_for(world, args)
     nx, ny, nz = grid
     z0, z1 = slabs.slab_bounds(nz, world, rank)
     lo, hi = slabs.resident_planes(z0, z1, nz)
@@ -337,6 +416,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ctx.synchronize()
 
+    # ---- set-up steps (not warm-up: first-touch allocations; for N>1 the cross-check of the two exchange paths)
     if world > 1 and args.exchange == "peers":
         # one step over NCCL first: it sizes the receive regions and is the cross-check of the peer path
         step()
@@ -350,11 +430,14 @@ def run_ours(args):
         if not np.array_equal(ctx.get_sites(), ref_sites):
             raise SystemExit("peer-memory exchange and NCCL all-gather disagree on the site numbering")
         del ref_sites
-    for _ in range(max(args.warmup, 3)):
+    else:
+        step()
+    # ---- W warm-up steps exactly as asked (the timing rules want W >= 3: the default; a smaller W is the caller's choice)
+    for _ in range(args.warmup):
         step()
     # ---- timed region: exactly K steps, CUDA events on the stream the kernels are launched on
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not sub else None
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -388,36 +471,6 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = nv_total / (ms_per_step * 1e-3)
 
-    if args.no_e2e:
-        if rank == 0:
-            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_per_step,
-                  "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world},
-                  "kernels": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-                  "ms_per_step_profiled": ms_prof / args.steps, "e2e": None, "note": "--no-e2e: device-resident legs only"})
-        ctx.close()
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
-    s = (z1 - z0, ny, nx)
-    outs = {
-        "inside": api.PinnedArray(s, np.uint8), "id": api.PinnedArray(s, np.int32), "d2": api.PinnedArray(s, np.uint32),
-        "edge3": api.PinnedArray((3,) + s, np.float32), "face3": api.PinnedArray((3,) + s, np.float32),
-        "cube": api.PinnedArray(s, np.float32), "radius": api.PinnedArray(s, np.float32),
-    }
-
-    def step_e2e():
-        if world == 1:
-            ctx.run_dense_host(pin_vol.array, outs["inside"].array, outs["id"].array, outs["d2"].array,
-                               outs["edge3"].array, outs["face3"].array, outs["cube"].array, outs["radius"].array)
-            return
-        ctx.upload_volume(pin_vol.array, zlo=lo)
-        step()
-        for k, which in (("inside", api.ARR_INSIDE), ("id", api.ARR_ID), ("d2", api.ARR_D2X4), ("edge3", api.ARR_EDGE3),
-                         ("face3", api.ARR_FACE3), ("cube", api.ARR_CUBE), ("radius", api.ARR_RADIUS)):
-            ctx.lib.vc_download(ctx.h, which, outs[k].array.ctypes.data)
-
     def time_e2e(fn):
         """seconds per call: median of individually timed calls (each call ends with its own stream syncs), max over ranks"""
         reps = max(3, min(args.steps, 10))
@@ -443,127 +496,163 @@ def run_ours(args):
         dist.all_reduce(t)
         return [int(v) for v in t]
 
-    e2e_planes_s = time_e2e(step_e2e)
-    h2d, d2h_planes = total(pin_vol.array.nbytes, sum(o.array.nbytes for o in outs.values()))
-    e2e_variants = {"all_planes": {"value": nv_total / e2e_planes_s, "ms_per_step": e2e_planes_s * 1e3, "h2d_bytes_per_step": h2d,
-                                   "d2h_bytes_per_step": d2h_planes,
-                                   "result": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32 for every grid vertex"}}
-    # ---- e2e, compact product (the headline): pinned host volume in; occupancy bit rows + one record
-    # (vertex, id, 4d2, 7 lambda, radius) per INSIDE vertex out.  Measures anchored at outside vertices are 0
-    # by definition, so nothing is lost; the dense planes are still computed in HBM.
-    e2e_s, d2h = e2e_planes_s, d2h_planes
-    if world == 1 or state.get("peers") is not None:
-        del outs
-        n_in = ctx.compact_count()
-        cap = n_in + 1024
-        wr = nx // 32 + 1
-        # the record arrays are the rows of ONE pinned 11 x cap block (vert | id | 4d2 | 7 lambda | radius): a z chunk's
-        # records then come back in a single 2-D copy
-        rec = api.PinnedArray((11, cap), np.uint32)
-        cb = {"bits": api.PinnedArray(((z1 - z0) * ny, wr), np.uint32), "vert": rec.array[0], "id": rec.array[1].view(np.int32),
-              "d2": rec.array[2], "lam": rec.array[3:10].view(np.float32), "rad": rec.array[10].view(np.float32)}
+    e2e, e2e_variants = None, {}
+    if not args.no_e2e:
+        (h2d,) = total(pin_vol.array.nbytes)
+        s3 = (z1 - z0, ny, nx)
+        small = nv_local <= 160_000_000  # the variants that return dense planes need 8..41 B of pinned memory per vertex
+        if small and not sub:
+            outs = {
+                "inside": api.PinnedArray(s3, np.uint8), "id": api.PinnedArray(s3, np.int32), "d2": api.PinnedArray(s3, np.uint32),
+                "edge3": api.PinnedArray((3,) + s3, np.float32), "face3": api.PinnedArray((3,) + s3, np.float32),
+                "cube": api.PinnedArray(s3, np.float32), "radius": api.PinnedArray(s3, np.float32),
+            }
 
-        def step_compact(dense=None):
-            # on a slab ctx the same call uploads the rank's planes and exchanges the site records over peer memory
-            return ctx.run_dense_host_compact(pin_vol.array, cap, cb["bits"].array, cb["vert"], cb["id"], cb["d2"], cb["lam"], cb["rad"],
-                                              *(dense or (None, None)))
+            def step_e2e():
+                if world == 1:
+                    ctx.run_dense_host(pin_vol.array, outs["inside"].array, outs["id"].array, outs["d2"].array,
+                                       outs["edge3"].array, outs["face3"].array, outs["cube"].array, outs["radius"].array)
+                    return
+                ctx.upload_volume(pin_vol.array, zlo=lo)
+                step()
+                for k, which in (("inside", api.ARR_INSIDE), ("id", api.ARR_ID), ("d2", api.ARR_D2X4), ("edge3", api.ARR_EDGE3),
+                                 ("face3", api.ARR_FACE3), ("cube", api.ARR_CUBE), ("radius", api.ARR_RADIUS)):
+                    ctx.lib.vc_download(ctx.h, which, outs[k].array.ctypes.data)
 
-        e2e_s = time_e2e(step_compact)
-        (d2h,) = total(int(cb["bits"].array.nbytes + n_in * 44))
-        (n_in_total,) = total(n_in)
-        # the e2e result really is the device result: spot-check the records against the resident planes
-        got_n, _ = step_compact()
-        step()  # the dense planes (the compact step computes the records of few inside vertices directly)
-        ctx.synchronize()
-        ids_dev = ctx.download(api.ARR_ID).ravel()
-        cube_dev = ctx.download(api.ARR_CUBE).ravel()
-        v = cb["vert"][:got_n]
-        if got_n != n_in or not (np.array_equal(cb["id"][:got_n], ids_dev[v]) and np.array_equal(cb["lam"][6, :got_n], cube_dev[v])):
-            raise SystemExit("compact e2e records disagree with the dense planes")
-        del ids_dev, cube_dev
-        e2e_variants["compact"] = {"value": nv_total / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                   "inside_vertices": n_in_total,
-                                   "result": "occupancy bit rows + (vertex u32, id i32, 4d2 u32, 7 lambda f32, radius f32) per inside vertex"}
-        if world == 1:
-            # the same pass from an MRC mode 0 (signed byte) volume -- a format the reference's reader takes as well
-            # (isosurface_tao/reader.h:235-239); the synthetic field is quantised to 1/16, which moves the surface a
-            # little, so this is another volume, timed for what the narrower upload buys
-            v8 = api.PinnedArray(pin_vol.array.shape, np.int8)
-            v8.array[...] = np.clip(np.rint(pin_vol.array * 16.0), -127, 127).astype(np.int8)
-            ctx.upload_volume(v8.array)
-            ctx.classify_grid(fetch=False)
-            cap8 = ctx.compact_count() + 1024
-            rec8 = api.PinnedArray((11, cap8), np.uint32)
-            dt8 = time_e2e(lambda: ctx.run_dense_host_compact(v8.array, cap8, cb["bits"].array, rec8.array[0], rec8.array[1].view(np.int32),
-                                                              rec8.array[2], rec8.array[3:10].view(np.float32),
-                                                              rec8.array[10].view(np.float32)))
-            e2e_variants["compact_int8_volume"] = {"value": nv_total / dt8, "ms_per_step": dt8 * 1e3, "h2d_bytes_per_step": int(v8.array.nbytes),
-                                                   "d2h_bytes_per_step": int(cb["bits"].array.nbytes + (cap8 - 1024) * 44),
-                                                   "result": "compact product from an MRC mode 0 (int8) volume (field quantised to 1/16)"}
-            del v8, rec8
-        dense = (api.PinnedArray((z1 - z0, ny, nx), np.int32), api.PinnedArray((z1 - z0, ny, nx), np.uint32))
-        dt = time_e2e(lambda: step_compact((dense[0].array, dense[1].array)))
-        e2e_variants["compact_plus_dense_ids"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
-                                                  "d2h_bytes_per_step": d2h + 8 * nv_total,
-                                                  "result": "compact product + id i32 and 4d2 u32 planes for every grid vertex"}
-        del dense
+            dt = time_e2e(step_e2e)
+            (d2h_planes,) = total(sum(o.array.nbytes for o in outs.values()))
+            e2e_variants["all_planes"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+                                          "d2h_bytes_per_step": d2h_planes,
+                                          "result": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32 for every grid vertex"}
+            del outs
+        # ---- e2e, compact product (the headline): pinned host volume in; occupancy bit rows + one record
+        # (vertex, id, 4d2, 7 lambda, radius) per INSIDE vertex out.  Measures anchored at outside vertices are 0
+        # by definition, so nothing is lost; on a slab ctx the same call uploads the rank's
+        # planes and exchanges the site records over peer memory.
+        if world == 1 or state.get("peers") is not None:
+            n_in = ctx.compact_count()
+            cap = n_in + 1024
+            wr = nx // 32 + 1
+            # the record arrays are the rows of ONE pinned 11 x cap block (vert | id | 4d2 | 7 lambda | radius): a z chunk's
+            # records then come back in a single 2-D copy
+            rec = api.PinnedArray((11, cap), np.uint32)
+            cb = {"bits": api.PinnedArray(((z1 - z0) * ny, wr), np.uint32), "vert": rec.array[0], "id": rec.array[1].view(np.int32),
+                  "d2": rec.array[2], "lam": rec.array[3:10].view(np.float32), "rad": rec.array[10].view(np.float32)}
 
+            def step_compact(dense=None):
+                return ctx.run_dense_host_compact(pin_vol.array, cap, cb["bits"].array, cb["vert"], cb["id"], cb["d2"], cb["lam"], cb["rad"],
+                                                  *(dense or (None, None)))
+
+            e2e_s = time_e2e(step_compact)
+            (d2h,) = total(int(cb["bits"].array.nbytes + n_in * 44))
+            (n_in_total,) = total(n_in)
+            # the e2e result really is the device result: spot-check the records against the resident planes
+            got_n, _ = step_compact()
+            step()  # the dense planes (the compact step computes the records of few inside vertices directly)
+            ctx.synchronize()
+            zc = min(z1 - z0, 128)  # a band of planes is enough for the cross-check (and bounded in host memory)
+            ids_dev = ctx.download_planes(api.ARR_ID, z0, z0 + zc).ravel()
+            cube_dev = ctx.download_planes(api.ARR_CUBE, z0, z0 + zc).ravel()
+            v = cb["vert"][:got_n]
+            m = v < ids_dev.size
+            if got_n != n_in or not (np.array_equal(cb["id"][:got_n][m], ids_dev[v[m]]) and
+                                     np.array_equal(cb["lam"][6, :got_n][m], cube_dev[v[m]])):
+                raise SystemExit("compact e2e records disagree with the dense planes")
+            del ids_dev, cube_dev
+            result = "occupancy bit rows + (vertex u32, id i32, 4d2 u32, 7 lambda f32, radius f32) per inside vertex"
+            e2e_variants["compact"] = {"value": nv_total / e2e_s, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+                                       "d2h_bytes_per_step": d2h, "inside_vertices": n_in_total, "result": result}
+            e2e = {"value": nv_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_s * 1e3, "result": result}
+            if world == 1 and small and not sub:
+                # the same pass from an MRC mode 0 (signed byte) volume -- a format the reference's reader takes as well
+                # (isosurface_tao/reader.h:235-239); the synthetic field is quantised to 1/16, which moves the surface a
+                # little, so this is another volume, timed for what the narrower upload buys
+                v8 = api.PinnedArray(pin_vol.array.shape, np.int8)
+                v8.array[...] = np.clip(np.rint(pin_vol.array * 16.0), -127, 127).astype(np.int8)
+                ctx.upload_volume(v8.array)
+                ctx.classify_grid(fetch=False)
+                cap8 = ctx.compact_count() + 1024
+                rec8 = api.PinnedArray((11, cap8), np.uint32)
+                dt8 = time_e2e(lambda: ctx.run_dense_host_compact(v8.array, cap8, cb["bits"].array, rec8.array[0], rec8.array[1].view(np.int32),
+                                                                  rec8.array[2], rec8.array[3:10].view(np.float32),
+                                                                  rec8.array[10].view(np.float32)))
+                e2e_variants["compact_int8_volume"] = {"value": nv_total / dt8, "ms_per_step": dt8 * 1e3, "h2d_bytes_per_step": int(v8.array.nbytes),
+                                                       "d2h_bytes_per_step": int(cb["bits"].array.nbytes + (cap8 - 1024) * 44),
+                                                       "result": "compact product from an MRC mode 0 (int8) volume (field quantised to 1/16)"}
+                del v8, rec8
+                ctx.upload_volume(pin_vol.array, zlo=lo)
+                ctx.classify_grid(fetch=False)
+            if small and not sub:
+                dense = (api.PinnedArray(s3, np.int32), api.PinnedArray(s3, np.uint32))
+                dt = time_e2e(lambda: step_compact((dense[0].array, dense[1].array)))
+                e2e_variants["compact_plus_dense_ids"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+                                                          "d2h_bytes_per_step": d2h + 8 * nv_total,
+                                                          "result": "compact product + id i32 and 4d2 u32 planes for every grid vertex"}
+                del dense
+        elif "all_planes" in e2e_variants:
+            ap = e2e_variants["all_planes"]
+            e2e = {"value": ap["value"], "unit": UNIT, "h2d_bytes_per_step": ap["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": ap["d2h_bytes_per_step"], "ms_per_step": ap["ms_per_step"], "result": ap["result"]}
+
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel of the profiled region
         steps = args.steps
+        wname = f"{fam}{nx}x{ny}x{nz}"
         kern = {k: {"ms_per_launch": v["ms"] / max(v["launches"], 1), "launches_per_step": v["launches"] / steps,
                     "ms_per_step": v["ms"] / steps} for k, v in prof.items()}
-        dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
-        planes_c = (min(z1 + 1, nz) - z0)
-        unit_bytes = {  # bytes one launch must move by the kernel's own contract
-            "classify_f32": 5 * nx * ny * (hi - lo),
-            "cell_measures": BYTES_MEASURES * nv_local,
-            "edt_pass_z": 8 * (nx + 1) * (ny + 1) * planes_c,
-            "edt_pass_x": 8 * ((nx + 1) * (ny + 1) + nx * (ny + 1)) * planes_c,
-            "edt_pass_y": 8 * (nx * (ny + 1) + nx * ny) * planes_c,
-        }
+        # roofline on SURVEY 8(d)'s algorithmic bytes: 5 / 8 / 32 B per grid vertex for classify / closest (passes Z+X+Y
+        # together) / measures, x the vertices this rank's launches process, / the event-timed duration
+        stage_ms = {}
+        for k, v in kern.items():
+            if k in STAGE_OF:
+                stage_ms[STAGE_OF[k]] = stage_ms.get(STAGE_OF[k], 0.0) + v["ms_per_step"]
+        stages = {st: {"bytes_per_vertex": STAGE_BYTES[st], "ms_per_step": t, "achieved": STAGE_BYTES[st] * nv_local / (t * 1e-3) / 1e9,
+                       "frac": STAGE_BYTES[st] * nv_local / (t * 1e-3) / 1e9 / peak} for st, t in stage_ms.items() if t > 0}
         roof = None
-        traffic, traffic_src, sm_pct = None, None, None
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's whole-grid launch, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if tj.get("workload") == f"{fam}{nx}x{ny}x{nz}" and dom in tj["kernels"]:
-                k = tj["kernels"][dom]
-                traffic = (k["dram_read_gb"] + k["dram_write_gb"]) * 1e9
-                traffic_src, sm_pct = tj["source"], k.get("sm_throughput_pct")
-        except Exception:
-            pass
-        if dom in unit_bytes:
-            ach = unit_bytes[dom] / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": traffic_src, "sm_throughput_pct_ncu": sm_pct, "peak_source": peak_src, "bytes_per_launch": unit_bytes[dom],
-                    "ms_per_launch": kern[dom]["ms_per_launch"], "share_of_step": kern[dom]["ms_per_step"] / (ms_prof / steps),
-                    "note": "bytes_per_launch is the kernel's dense contract (8 B in + 8 B out per element of its planes); pass X reads "
-                            "only the columns that hold sites (column bitmap), so its DRAM traffic can be below it"}
+        hot = [k for k in kern if k in STAGE_OF]
+        if hot:
+            dom = max(hot, key=lambda k: kern[k]["ms_per_step"])
+            st = STAGE_OF[dom]
+            nbytes = STAGE_BYTES[st] * nv_local  # the whole stage's algorithmic bytes are charged to its dominant kernel
+            ach = nbytes / (kern[dom]["ms_per_step"] * 1e-3) / 1e9
+            traffic, traffic_src, sm_pct = load_traffic(wname if world == 1 else f"{wname}/slab{world}", dom)
+            roof = {"kernel": dom, "stage": st, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "sm_throughput_pct_ncu": sm_pct, "peak_source": peak_src,
+                    "bytes_per_launch": nbytes, "ms_per_launch": kern[dom]["ms_per_step"],
+                    "share_of_step": kern[dom]["ms_per_step"] / (ms_prof / steps),
+                    "stage_frac": stages[st]["frac"],
+                    "note": f"achieved = SURVEY 8(d) bytes of the {st} stage ({STAGE_BYTES[st]} B/vertex x {nv_local} vertices) / this kernel's "
+                            "event-timed duration per step; stage_frac divides the same bytes by the whole stage's kernels"}
         pipe_ach = BYTES_PIPELINE * nv_local / (ms_per_step * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64/f32",
             "data": "synthetic",
-            "config": {"workload": f"{fam}{nx}x{ny}x{nz}", "sites": state["nsites"], "z_slabs": world, "slab_heights": "equal" if args.balance <= 0 else f"balanced (1 + {args.balance} x inside fraction)",
+            "config": {"workload": wname, "sites": state["nsites"], "z_slabs": world,
+                       "slab_heights": "equal" if args.balance <= 0 else f"balanced (1 + {args.balance} x inside fraction)",
                        "vertices_per_gpu": nv_local,
                        "exchange": ("none (one slab)" if world == 1 else
                                     "peer memory: detection kernel stores records into every rank over NVLink (vc_peer.cu)"
                                     if state.get("peers") is not None else "NCCL all-gather"), "l2": "inputs larger than L2 (no flush needed)",
-                       "outputs": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32"},
-            "e2e": {"value": nv_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3,
-                    "result": e2e_variants.get("compact", e2e_variants["all_planes"])["result"]},
+                       "outputs": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32 (resident in HBM)",
+                       "e2e_result": e2e["result"] if e2e else None},
+            "e2e": e2e,
             "e2e_variants": e2e_variants,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "roofline_stages": stages,
             "roofline_pipeline": {"bound": "hbm", "bytes_per_vertex": BYTES_PIPELINE, "achieved": pipe_ach, "peak": peak,
                                   "unit": "GB/s", "frac": pipe_ach / peak, "note": "45 B/vertex (SURVEY 8d) x vertices / step time, per GPU"},
             "kernels": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
             "ms_per_step_profiled": ms_prof / steps,
         }
-        if world == 1 and fam == "twist":
+        if sub:
+            line = {k: line[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "e2e_variants", "gpu_launches", "roofline",
+                                         "roofline_stages", "roofline_pipeline", "kernels", "ms_per_step_profiled")}
+        if world == 1 and fam == "twist" and not args.no_e2e:
             # stage 1' (new functionality, no reference counterpart): the same pass starting from the closed triangle
             # mesh of the twisted plate instead of a voxel volume -- parity classification, then sites / closest / measures
             try:
@@ -577,7 +666,6 @@ def run_ours(args):
                     ctx.classify_mesh(mv, mt, fetch=False)
                     ns_mesh = ctx.run_dense()
                     ts.append(time.perf_counter() - t0)
-                mprof = {}
                 ctx.profile(True)
                 ctx.profile_reset()
                 ctx.classify_mesh(mv, mt, fetch=False)
@@ -589,14 +677,57 @@ def run_ours(args):
                                              "each step) + sites + closest + measures; wall clock per step"}
             except Exception as ex:
                 line["mesh_path"] = {"error": repr(ex)}
+    barrier()
+    if state.get("peers") is not None:
+        state["peers"].close()
+    ctx.close()
+    del pin_vol
+    return line
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = None
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
+    # stdout must carry ONE line (rank 0's JSON): anything a library prints there meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fam, grid, scaling = workload_for(world, args)
+    line = measure(args, fam, grid, scaling, dist, rank, world, local)
+    if rank == 0:
+        line["numa"] = numa
+    default_workload = not (args.grid or args.workload or args.weak)
+    if world == 1 and default_workload and not args.no_at512:
+        # BASELINE configs[2], the 512^3 configuration the metric's single-GPU target (>= 1e10 vertices/s end to end) is quoted on
+        line["at_512"] = measure(args, AT_512[0], AT_512[1], "strong", None, 0, 1, local, sub=True)
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 with quiet_stdout():
-                    line["cpu_baseline"] = cpu_reference_rate(fam, grid, budget_s=20.0)
+                    line["cpu_baseline"] = cpu_reference_rate(fam, grid, budget_s=15.0)
             except Exception as ex:  # the checker missing must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
         emit(line)
-    ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -611,10 +742,13 @@ def main():
     ap.add_argument("--workload", default=None, help="sphere256 | torus256 | twist512 | assembly1024 ...")
     ap.add_argument("--grid", default=None, help="NX,NY,NZ (assembly family)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weak", action="store_true", help="weak scaling instead: 512^3 vertices per GPU (twist512 at N=1, assembly family "
+                    "512x512x1024 / 512x1024x1024 / 1024^3 at N=2/4/8)")
+    ap.add_argument("--no-at512", action="store_true", help="N=1: skip the secondary twist512 measurement")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--balance", type=float, default=0.0, help="EXPERIMENTAL, N>1: weight c of the per-plane inside fraction in the "
                     "slab-height estimate 1 + c*fraction (0 = equal heights, the default)")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (very large grids: the all-planes leg needs "
-                    "41 B of pinned host memory per grid vertex)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
     ap.add_argument("--exchange", default="peers", choices=["peers", "nccl"],
                     help="N>1: how the site records travel between ranks (peer-memory kernel stores, or NCCL all-gather)")
     args = ap.parse_args()

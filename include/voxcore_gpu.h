@@ -124,13 +124,17 @@ int vc_sites_import_global(vc_ctx* ctx, const uint64_t* keys, const uint64_t* co
  *   vc_peer_open_ptrs  same for contexts living in ONE process: bases[p] = vc_peer_buffer of rank p.
  * Per exchange (needs vc_classify_grid): vc_sites_post_peers is asynchronous; vc_sites_collect_peers
  * waits for all ranks' records, numbers the union (same result as vc_sites_import_global) and
- * returns the global site count.  A rank that never posts turns into VC_ERR_STATE after ~2 s, a
- * rank with more than `cap` records into VC_ERR_NOMEM; neither hangs. */
+ * returns the global site count.  `cap` and `world` must agree on every rank (the region offsets are computed from
+ * them; a mismatch is detected at collect time: VC_ERR_INVALID).  A rank that has not posted within the time bound
+ * (vc_peer_set_timeout, else the environment variable VC_PEER_TIMEOUT_MS, else 10 s) turns into VC_ERR_STATE -- the
+ * post stays pending and vc_sites_collect_peers may simply be called again -- a rank with more than `cap` records
+ * into VC_ERR_NOMEM; neither hangs. */
 int vc_peer_create(vc_ctx* ctx, int world, int rank, int64_t cap, void* handle_out);
 int vc_peer_open(vc_ctx* ctx, const void* handles);
 int vc_peer_open_ptrs(vc_ctx* ctx, void* const* bases);
 void* vc_peer_buffer(vc_ctx* ctx);
 int vc_peer_close(vc_ctx* ctx);
+int vc_peer_set_timeout(vc_ctx* ctx, int64_t milliseconds);
 int vc_sites_post_peers(vc_ctx* ctx);
 int vc_sites_collect_peers(vc_ctx* ctx, int64_t* n_all);
 

@@ -113,10 +113,37 @@ int64_t orc_extract_sites(const uint8_t* inside, int nx, int ny, int nz, float* 
                     for (int i = i0; i < i0 + 64 && i < nx; ++i)
                         zf[((size_t)i * ny + j) * nz + k] = inside[IDX(i, j, k)];
 #define ZF(i, j, k) zf[((size_t)(i) * ny + (j)) * nz + (k)]
+    /* Rows (i, j, all k) in which no voxel differs from any of its 6 neighbours emit nothing, so the scan may step
+     * over them: rowflag marks the others.  A row is quiet iff it is constant, equals its 4 neighbour rows, and --
+     * where a neighbour is out of bounds (read as 0, include/spaceinfo.h:125) -- is all 0.  (Same output, same
+     * order: only rows that would not have emitted are skipped; the marking runs on all cores.) */
+    uint8_t* rowflag = (uint8_t*)malloc((size_t)nx * ny);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+        {
+            const uint8_t* r = &ZF(i, j, 0);
+            int quiet = nz < 2 || memcmp(r, r + 1, (size_t)nz - 1) == 0; /* constant along z */
+            const int border = i == 0 || i == nx - 1 || j == 0 || j == ny - 1;
+            if (quiet && (border || nz >= 1) && r[0] != 0) /* the z ends (k = -1, k = nz) and any side border read 0 */
+                quiet = 0;
+            if (quiet && i > 0)
+                quiet = memcmp(r, &ZF(i - 1, j, 0), nz) == 0;
+            if (quiet && i < nx - 1)
+                quiet = memcmp(r, &ZF(i + 1, j, 0), nz) == 0;
+            if (quiet && j > 0)
+                quiet = memcmp(r, &ZF(i, j - 1, 0), nz) == 0;
+            if (quiet && j < ny - 1)
+                quiet = memcmp(r, &ZF(i, j + 1, 0), nz) == 0;
+            rowflag[(size_t)i * ny + j] = (uint8_t)!quiet;
+        }
     uint8_t* seen = (uint8_t*)calloc(cx * cy * cz, 1);
     int64_t n = 0;
     for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j)
+        {
+            if (!rowflag[(size_t)i * ny + j])
+                continue;
             for (int k = 0; k < nz; ++k)
             {
                 int cur = ZF(i, j, k);
@@ -147,8 +174,10 @@ int64_t orc_extract_sites(const uint8_t* inside, int nx, int ny, int nz, float* 
                     }
                 }
             }
+        }
 #undef ZF
     free(seen);
+    free(rowflag);
     free(zf);
     return n;
 }

@@ -407,11 +407,22 @@ def test_peer_exchange_errors_do_not_hang(ctx_factory):
         return a, b
 
     a, b = pair(20000)
+    a.peer_set_timeout(300)
     a.sites_post_peers()
     with pytest.raises(api.VoxcoreError, match="timed out"):
         a.sites_collect_peers()  # b has not posted
     b.sites_post_peers()
-    assert b.sites_collect_peers() == len(ob.extract_sites(ob.classify_grid(vol)))  # a's post is still there
+    nref = len(ob.extract_sites(ob.classify_grid(vol)))
+    assert b.sites_collect_peers() == nref  # a's post is still there
+    assert a.sites_collect_peers() == nref  # ... and a's own exchange is still collectable after its time-out
+    # ranks created with different capacities would overwrite each other's regions: detected, not silent
+    a, b = pair(20000)
+    b.peer_create(2, 1, 10000)
+    bases = [a.peer_buffer(), b.peer_buffer()]
+    with pytest.raises(api.VoxcoreError, match="another capacity"):
+        a.peer_open_ptrs(bases)
+    with pytest.raises(api.VoxcoreError, match="not mapped"):
+        a.sites_post_peers()  # nothing is ever stored into a buffer laid out differently
     a, b = pair(16)
     a.sites_post_peers()
     b.sites_post_peers()

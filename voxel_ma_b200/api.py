@@ -24,7 +24,7 @@ SYMBOLS = [
     "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_i8", "vc_volume_upload_f64_zfast",
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
-    "vc_peer_buffer", "vc_peer_close", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
+    "vc_peer_buffer", "vc_peer_close", "vc_peer_set_timeout", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_closest_points_f32", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
     "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_download_planes", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records",
     "vc_run_dense_host_compact", "vc_run_dense_host_compact_i8", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
@@ -83,6 +83,7 @@ def load_library(path: str | None = None):
     lib.vc_peer_buffer.argtypes = [vp]
     lib.vc_peer_buffer.restype = vp
     lib.vc_peer_close.argtypes = [vp]
+    lib.vc_peer_set_timeout.argtypes = [vp, i64]
     lib.vc_sites_post_peers.argtypes = [vp]
     lib.vc_sites_collect_peers.argtypes = [vp, C.POINTER(i64)]
     lib.vc_set_compact_mode.argtypes = [vp, i32]
@@ -199,9 +200,15 @@ class Context:
         (MRC mode 0)."""
         i8 = vol.dtype == np.int8
         v = np.ascontiguousarray(vol, np.int8 if i8 else np.float32)
+        if v.ndim != 3:
+            raise ValueError(f"upload_volume wants [z][y][x] planes, got shape {v.shape}")
         if not self.nx:
             nz, ny, nx = v.shape
             self.set_grid(nx, ny, nz)
+        if v.shape[1:] != (self.ny, self.nx):  # a stale grid would be read with the wrong row length: silently wrong results
+            raise ValueError(f"volume planes are {v.shape[1:]} but the context's grid is {(self.ny, self.nx)} (y, x): call set_grid first")
+        if zlo < 0 or zlo + v.shape[0] > self.nz:
+            raise ValueError(f"planes [{zlo}, {zlo + v.shape[0]}) lie outside the grid's {self.nz} planes")
         fn = self.lib.vc_volume_upload_i8 if i8 else self.lib.vc_volume_upload_f32
         self._ck(fn(self.h, _ptr(v), zlo, zlo + v.shape[0]))
 
@@ -281,6 +288,10 @@ class Context:
 
     def peer_buffer(self) -> int:
         return self.lib.vc_peer_buffer(self.h)
+
+    def peer_set_timeout(self, milliseconds: int) -> None:
+        """bound of the wait for the other ranks' posts (default 10 s / VC_PEER_TIMEOUT_MS)"""
+        self._ck(self.lib.vc_peer_set_timeout(self.h, int(milliseconds)))
 
     def peer_close(self) -> None:
         self._ck(self.lib.vc_peer_close(self.h))
@@ -421,7 +432,23 @@ class Context:
     def device_ptr(self, which) -> int:
         return int(self.lib.vc_device_ptr(self.h, which) or 0)
 
+    @staticmethod
+    def _host_buf(a, dtype, count, what):
+        """the C ABI takes raw host pointers: a wrong dtype, a strided view or a short array would make the copies read or
+        write past the buffer"""
+        if a is None:
+            return
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous or a.size < count:
+            raise ValueError(f"{what}: need a C-contiguous {np.dtype(dtype).name} array of >= {count} elements, got "
+                             f"{getattr(a, 'dtype', type(a))} {getattr(a, 'shape', '')}")
+
     def run_dense_host(self, vol, inside=None, ids=None, d2x4=None, edge3=None, face3=None, cube=None, radius=None) -> int:
+        nv = self.nx * self.ny * self.nz
+        self._host_buf(vol, np.float32, nv, "vol")
+        for a, dt, k, what in ((inside, np.uint8, 1, "inside"), (ids, np.int32, 1, "ids"), (d2x4, np.uint32, 1, "d2x4"),
+                               (edge3, np.float32, 3, "edge3"), (face3, np.float32, 3, "face3"), (cube, np.float32, 1, "cube"),
+                               (radius, np.float32, 1, "radius")):
+            self._host_buf(a, dt, k * nv, what)
         n = C.c_int64()
         self._ck(self.lib.vc_run_dense_host(self.h, _ptr(vol), _ptr(inside), _ptr(ids), _ptr(d2x4), _ptr(edge3),
                                             _ptr(face3), _ptr(cube), _ptr(radius), C.byref(n)))
@@ -448,6 +475,18 @@ class Context:
     def run_dense_host_compact(self, vol, cap, inside_bits=None, vert=None, ids=None, d2x4=None, lambda7=None, radius=None,
                                id_dense=None, d2x4_dense=None):
         """-> (n_inside, n_sites).  lambda7 must be laid out [7][cap]."""
+        planes = self.z1 - self.z0
+        nres = (min(self.z1 + 1, self.nz) - max(self.z0 - 1, 0)) * self.ny * self.nx  # the slab's resident voxel planes
+        self._host_buf(vol, np.int8 if vol.dtype == np.int8 else np.float32, nres, "vol")
+        self._host_buf(inside_bits, np.uint32, planes * self.ny * (self.nx // 32 + 1), "inside_bits")
+        for a, dt, k, what in ((vert, np.uint32, cap, "vert"), (ids, np.int32, cap, "ids"), (d2x4, np.uint32, cap, "d2x4"),
+                               (radius, np.float32, cap, "radius"), (id_dense, np.int32, planes * self.ny * self.nx, "id_dense"),
+                               (d2x4_dense, np.uint32, planes * self.ny * self.nx, "d2x4_dense")):
+            self._host_buf(a, dt, k, what)
+        if lambda7 is not None:
+            self._host_buf(lambda7, np.float32, 7 * cap, "lambda7")
+            if lambda7.shape != (7, cap):
+                raise ValueError(f"lambda7 must be laid out [7][cap] = (7, {cap}), got {lambda7.shape}")
         n, ns = C.c_int64(), C.c_int64()
         fn = self.lib.vc_run_dense_host_compact_i8 if vol.dtype == np.int8 else self.lib.vc_run_dense_host_compact
         self._ck(fn(self.h, _ptr(vol), _ptr(inside_bits), cap, C.byref(n), _ptr(vert), _ptr(ids),

@@ -341,6 +341,8 @@ extern "C"
         DevBuf dk, dc;
         const u64* pk = (const u64*)keys;
         const u64* pc = (const u64*)corners;
+        if (n > 0 && vc_is_device_ptr(keys) != vc_is_device_ptr(corners))
+            return vc_fail(c, VC_ERR_INVALID, "vc_sites_import_global: keys and corners must both be host or both be device pointers");
         if (n > 0 && !vc_is_device_ptr(keys))
         {
             VC_CUDA(c, dk.ensure((size_t)n * 8));
@@ -405,9 +407,10 @@ extern "C"
             int ci[3];
             for (int d = 0; d < 3; ++d)
             {
-                float f = xyz[3 * i + d] + 0.5f;
-                int k = (int)f;
-                if (!(f == (float)k) || k < 0 || k > lim[d] || xyz[3 * i + d] != (float)k - 0.5f)
+                const float f = xyz[3 * i + d] + 0.5f;
+                // range first: a cast of NaN / inf / a huge value to int is undefined
+                const int k = (f >= 0.0f && f <= (float)lim[d]) ? (int)f : -1;
+                if (k < 0 || !(f == (float)k) || xyz[3 * i + d] != (float)k - 0.5f)
                     lattice = false;
                 ci[d] = k;
             }
@@ -423,9 +426,9 @@ extern "C"
             int s = st_finalize_sites(c, nullptr, dc.as<u64>(), n, false);
             cudaStreamSynchronize(c->stream);
             dc.release();
-            if (s != VC_OK)
+            if (s != VC_OK && s != VC_ERR_UNSUPPORTED) // more sites than the dense path's id fields hold: the cell list has no limit
                 return s;
-            if (c->lattice)
+            if (s == VC_OK && c->lattice)
                 return VC_OK;
         }
         return st_build_cell_list(c, xyz, n);
@@ -686,6 +689,7 @@ extern "C"
         c->zhi = c->nz;
         // H2D in plane chunks on the copy stream; classification of a chunk starts as soon as it lands
         const int chunk = c->nz >= 16 ? (c->nz + 7) / 8 : c->nz;
+        VcEvents events;
         cudaEvent_t ev[16];
         int nchunks = 0;
         for (int z = 0; z < c->nz; z += chunk, ++nchunks)
@@ -693,18 +697,15 @@ extern "C"
             int ze = z + chunk < c->nz ? z + chunk : c->nz;
             size_t off = plane * z, cnt = plane * (size_t)(ze - z);
             VC_CUDA(c, cudaMemcpyAsync(c->vol.as<float>() + off, vol + off, cnt * 4, cudaMemcpyDefault, c->s_h2d));
-            VC_CUDA(c, cudaEventCreateWithFlags(&ev[nchunks], cudaEventDisableTiming));
+            VC_CUDA(c, events.make(&ev[nchunks]));
             VC_CUDA(c, cudaEventRecord(ev[nchunks], c->s_h2d));
         }
         for (int i = 0; i < nchunks; ++i)
-        {
             VC_CUDA(c, cudaStreamWaitEvent(c->stream, ev[i], 0));
-            VC_CUDA(c, cudaEventDestroy(ev[i]));
-        }
         c->have_vol = true;
         VC_TRY(st_classify(c));
         cudaEvent_t done;
-        VC_CUDA(c, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        VC_CUDA(c, events.make(&done));
         auto d2h_after = [&](void* dst, const void* src, size_t bytes) -> int
         {
             if (!dst)
@@ -727,7 +728,6 @@ extern "C"
             VC_TRY(d2h_after(radius, c->radius.p, nv * 4));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         VC_CUDA(c, cudaStreamSynchronize(c->s_d2h));
-        VC_CUDA(c, cudaEventDestroy(done));
         if (nsites)
             *nsites = c->nsites;
         return VC_OK;

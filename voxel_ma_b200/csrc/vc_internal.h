@@ -114,7 +114,7 @@ struct vc_ctx
     double cl_org[3] = {0, 0, 0}, cl_h = 1.0;
     // peer exchange of the site records (vc_peer.cu): receive buffer of this rank, mapped buffers of the others
     int peer_world = 0, peer_rank = -1;
-    int64_t peer_cap = 0;
+    int64_t peer_cap = 0, peer_timeout_ms = 0; // bound of the wait for the other ranks' posts (0: VC_PEER_TIMEOUT_MS or 10 s)
     u64 peer_seq = 0;
     bool peer_posted = false, peer_ipc = false;
     void* peer_base[VC_MAX_PEERS] = {};
@@ -150,6 +150,24 @@ int vc_fail(vc_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
         if (_s != VC_OK)      \
             return _s;        \
     } while (0)
+
+// events that live for one API call: destroyed on every way out of it (error returns included)
+struct VcEvents
+{
+    std::vector<cudaEvent_t> v;
+    cudaError_t make(cudaEvent_t* e)
+    {
+        cudaError_t st = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if (st == cudaSuccess)
+            v.push_back(*e);
+        return st;
+    }
+    ~VcEvents()
+    {
+        for (auto e : v)
+            cudaEventDestroy(e);
+    }
+};
 
 // RAII launch bracket: counts the launch and, when profiling, records CUDA events on the ctx stream
 struct ProfScope

@@ -13,7 +13,9 @@
 //
 // Receive buffer of a rank (u64 units), double-buffered on the parity of the sequence number so a
 // fast rank's next exchange cannot overwrite what a slow rank is still packing:
-//     header  [2][VC_MAX_PEERS][8]      line (parity, source): [0] = sequence, [1] = record count
+//     header  [2][VC_MAX_PEERS][8]      line (parity, source): [0] = sequence, [1] = record count,
+//                                       [2] = the source's region capacity, [3] = its world size (checked by the receiver:
+//                                       region offsets are computed from them, ranks that disagree would overwrite each other)
 //     records [2][world][2 * cap]       region (parity, source): keys[cap] | corners[cap]
 // A rank may start exchange k+2 only after collecting k+1, i.e. after every rank posted k+1, which
 // each does after packing k (stream order): two buffers are enough.
@@ -21,8 +23,9 @@
 
 #include "vc_internal.h"
 
-#define PEER_HDR_U64 (2 * VC_MAX_PEERS * 8)
-#define PEER_SPIN_LIMIT (4000000000ll) // clock64 ticks (~2 s): a missing rank becomes an error, not a hang
+#define PEER_HDR_U64 (2 * VC_MAX_PEERS * 8 + 8) // the post lines, then one line of set-up facts: [0] = cap, [1] = world
+#define PEER_CFG_OFF (2 * VC_MAX_PEERS * 8)
+#define PEER_TIMEOUT_MS_DEFAULT 10000 // a missing rank becomes an error, not a hang (VC_PEER_TIMEOUT_MS / vc_peer_set_timeout)
 
 static size_t peer_rx_u64(int world, int64_t cap) { return (size_t)PEER_HDR_U64 + 2ull * world * 2ull * (size_t)cap; }
 static __host__ __device__ inline size_t peer_hdr_off(int parity, int src) { return ((size_t)parity * VC_MAX_PEERS + src) * 8; }
@@ -37,7 +40,7 @@ struct VcPeerHdr
 };
 
 // one warp: lane p tells rank p how many records this rank wrote (after they are visible system-wide)
-__global__ void k_peer_post(VcPeerHdr hdr, int world, const u64* __restrict__ counter, u64 seq)
+__global__ void k_peer_post(VcPeerHdr hdr, int world, const u64* __restrict__ counter, u64 seq, u64 cap)
 {
     const int p = threadIdx.x;
     if (p >= world)
@@ -46,12 +49,21 @@ __global__ void k_peer_post(VcPeerHdr hdr, int world, const u64* __restrict__ co
     __threadfence_system();
     u64* line = hdr.line[p];
     line[1] = n;
+    line[2] = cap;
+    line[3] = (u64)world;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(line), "l"(seq) : "memory");
 }
 
 // one warp: lane p waits for rank p's post of `seq` in MY header, then the warp turns the counts into
-// offsets.  res[0] = total, res[1] = status (0 ok, 1 timeout, 2 a region overflowed), off[p] = start of p.
-__global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, u64 cap, u64* __restrict__ off,
+// offsets.  res[0] = total, res[1] = status (0 ok, 1 timeout, 2 a region overflowed, 3 a rank was set up with another
+// capacity / world size), off[p] = start of p.  The wait is bounded in TIME (%globaltimer, nanoseconds).
+__device__ __forceinline__ u64 vc_globaltimer()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, u64 cap, u64 timeout_ns, u64* __restrict__ off,
                             u64* __restrict__ res)
 {
     const int p = threadIdx.x;
@@ -60,14 +72,14 @@ __global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, 
     if (p < world)
     {
         const u64* line = my_hdr + p * 8;
-        const long long t0 = clock64();
+        const u64 t0 = vc_globaltimer();
         for (;;)
         {
             u64 s;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(line) : "memory");
             if (s == seq)
                 break;
-            if (clock64() - t0 > PEER_SPIN_LIMIT)
+            if (vc_globaltimer() - t0 > timeout_ns)
             {
                 bad = 1;
                 break;
@@ -76,8 +88,13 @@ __global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, 
         }
         if (!bad)
         {
+            u64 pcap, pworld;
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(n) : "l"(line + 1) : "memory");
-            if (n > cap)
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pcap) : "l"(line + 2) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pworld) : "l"(line + 3) : "memory");
+            if (pcap != cap || pworld != (u64)world)
+                bad = 3;
+            else if (n > cap)
                 bad = 2;
         }
     }
@@ -145,11 +162,18 @@ extern "C"
         const size_t bytes = peer_rx_u64(world, cap) * 8;
         VC_CUDA(c, c->peer_rx.ensure(bytes));
         VC_CUDA(c, cudaMemset(c->peer_rx.p, 0, bytes)); // sequence numbers start at 0; the first exchange posts 1
+        const u64 cfg[2] = {(u64)cap, (u64)world}; // read by every rank that maps this buffer (peer_check_cfg)
+        VC_CUDA(c, cudaMemcpy((u64*)c->peer_rx.p + PEER_CFG_OFF, cfg, sizeof cfg, cudaMemcpyHostToDevice));
         VC_CUDA(c, c->peer_all.ensure((size_t)world * 2ull * (size_t)cap * 8));
         c->peer_world = world;
         c->peer_rank = rank;
         c->peer_cap = cap;
         c->peer_seq = 0;
+        if (c->peer_timeout_ms <= 0)
+        {
+            const char* e = getenv("VC_PEER_TIMEOUT_MS");
+            c->peer_timeout_ms = e && atoll(e) > 0 ? atoll(e) : PEER_TIMEOUT_MS_DEFAULT;
+        }
         c->peer_base[rank] = c->peer_rx.p;
         if (handle_out)
         {
@@ -157,6 +181,23 @@ extern "C"
             VC_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_rx.p));
             static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
             memcpy(handle_out, &h, sizeof(h));
+        }
+        return VC_OK;
+    }
+
+    // a peer's receive buffer must have been created with this rank's capacity and world size: the offsets of the
+    // regions this rank stores into are computed from them
+    static int peer_check_cfg(vc_ctx* c, int p)
+    {
+        u64 cfg[2] = {0, 0};
+        VC_CUDA(c, cudaMemcpy(cfg, (const u64*)c->peer_base[p] + PEER_CFG_OFF, sizeof cfg, cudaMemcpyDefault));
+        if (cfg[0] != (u64)c->peer_cap || cfg[1] != (u64)c->peer_world)
+        {
+            if (c->peer_ipc)
+                cudaIpcCloseMemHandle(c->peer_base[p]);
+            c->peer_base[p] = nullptr;
+            return vc_fail(c, VC_ERR_INVALID, "a rank of the slab group was created with another capacity or world size "
+                                              "(vc_peer_create arguments must agree on every rank)");
         }
         return VC_OK;
     }
@@ -175,6 +216,8 @@ extern "C"
             void* base = nullptr;
             VC_CUDA(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
             c->peer_base[p] = base;
+            c->peer_ipc = true;
+            VC_TRY(peer_check_cfg(c, p));
         }
         c->peer_ipc = true;
         return VC_OK;
@@ -201,12 +244,21 @@ extern "C"
                 cudaGetLastError();
             }
             c->peer_base[p] = bases[p];
+            VC_TRY(peer_check_cfg(c, p));
         }
         c->peer_ipc = false;
         return VC_OK;
     }
 
     void* vc_peer_buffer(vc_ctx* c) { return c ? c->peer_rx.p : nullptr; }
+
+    int vc_peer_set_timeout(vc_ctx* c, int64_t milliseconds)
+    {
+        if (!c || milliseconds < 1)
+            return VC_ERR_INVALID;
+        c->peer_timeout_ms = milliseconds;
+        return VC_OK;
+    }
 
     int vc_peer_close(vc_ctx* c)
     {
@@ -244,7 +296,7 @@ extern "C"
         }
         u64* counter = c->scratch.as<u64>() + 2;
         VC_TRY(st_detect_sites_to_peers(c, dst, counter));
-        VC_LAUNCH(c, "peer_post", k_peer_post, 1, 32, 0, hdr, c->peer_world, counter, seq);
+        VC_LAUNCH(c, "peer_post", k_peer_post, 1, 32, 0, hdr, c->peer_world, counter, seq, (u64)c->peer_cap);
         VC_CUDA(c, cudaGetLastError());
         c->peer_seq = seq;
         c->peer_posted = true;
@@ -258,14 +310,13 @@ extern "C"
         if (!c->peer_posted)
             return vc_fail(c, VC_ERR_STATE, "vc_sites_collect_peers: nothing posted");
         VC_CUDA(c, cudaSetDevice(c->device));
-        c->peer_posted = false;
         const int world = c->peer_world;
         const int parity = (int)(c->peer_seq & 1);
         u64* base = (u64*)c->peer_rx.p;
         u64* off = c->scratch.as<u64>() + 4; // world + 1 offsets, then res[2]
         u64* res = off + VC_MAX_PEERS + 1;
         VC_LAUNCH(c, "peer_wait", k_peer_wait, 1, 32, 0, base + peer_hdr_off(parity, 0), world, c->peer_seq,
-                  (u64)c->peer_cap, off, res);
+                  (u64)c->peer_cap, (u64)c->peer_timeout_ms * 1000000ull, off, res);
         u64* keys = c->peer_all.as<u64>();
         u64* corners = keys + (size_t)world * (size_t)c->peer_cap;
         unsigned bx = vc_blocks((size_t)c->peer_cap, 256);
@@ -275,8 +326,13 @@ extern "C"
         u64* h = (u64*)c->pinned;
         VC_CUDA(c, cudaMemcpyAsync(h, res, 16, cudaMemcpyDeviceToHost, c->stream));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (h[1] == 1)
-            return vc_fail(c, VC_ERR_STATE, "vc_sites_collect_peers: timed out waiting for a rank of the slab group");
+        if (h[1] == 1) // the post stays pending: the records of this sequence are still collectable by calling again
+            return vc_fail(c, VC_ERR_STATE, "vc_sites_collect_peers: timed out waiting for a rank of the slab group (call again to "
+                                            "keep waiting; VC_PEER_TIMEOUT_MS / vc_peer_set_timeout set the bound)");
+        c->peer_posted = false;
+        if (h[1] == 3)
+            return vc_fail(c, VC_ERR_INVALID, "vc_sites_collect_peers: a rank of the slab group was created with another capacity or "
+                                              "world size (vc_peer_create arguments must agree on every rank)");
         if (h[1] == 2)
             return vc_fail(c, VC_ERR_NOMEM, "vc_sites_collect_peers: a rank produced more site records than the capacity given "
                                             "to vc_peer_create");

@@ -24,7 +24,7 @@ def balanced_bounds(weights, world: int) -> list[tuple[int, int]]:
     """Contiguous z-slabs of (nearly) equal total WEIGHT instead of equal height: weights[z] is an estimate of the work
     of vertex plane z (e.g. 1 + c * inside fraction: the measures of a plane cost more where it cuts solids).  Every slab
     gets at least one plane; returns [(z0, z1)] per rank.  Uniform weights reproduce slab_bounds up to the placement of
-    the remainder.  (Not yet used by bench.py: DESIGN.md section 8 lists it as the next lever for the 8-GPU step.)"""
+    the remainder.  Used by bench.py --balance."""
     w = np.asarray(weights, np.float64)
     nz = len(w)
     if world < 1 or world > nz or (w < 0).any():
