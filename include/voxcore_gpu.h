@@ -114,9 +114,10 @@ int vc_sites_detect_local(vc_ctx* ctx, int64_t* nlocal);
 int vc_sites_export_local(vc_ctx* ctx, uint64_t* keys_out, uint64_t* corners_out);
 int vc_sites_import_global(vc_ctx* ctx, const uint64_t* keys, const uint64_t* corners, int64_t n);
 /* The same exchange over peer memory (NVLink), without a collective library on the data path: the
- * detection kernel stores every record straight into the receive buffer of every rank of the slab
- * group, one warp posts (sequence, count) with a system-scope release, and a rank collects by
- * waiting on its own header (voxel_ma_b200/csrc/vc_peer.cu).  Set-up, once per group:
+ * records of a rank's own corner planes are sorted by key on that rank and stored as one sorted run straight
+ * into the receive buffer of every rank of the slab group, one warp posts (sequence, count) with a
+ * system-scope release, and a rank collects by waiting on its own header and merging the runs by
+ * ranking -- no rank sorts the union (voxel_ma_b200/csrc/vc_peer.cu).  Set-up, once per group:
  *   vc_peer_create   allocates this rank's receive buffer for `world` ranks x `cap` records each and
  *                    writes its 64-byte CUDA IPC handle to handle_out (nullable);
  *   vc_peer_open     maps the other ranks' buffers from `handles` (world x 64 bytes, rank order;
@@ -128,7 +129,7 @@ int vc_sites_import_global(vc_ctx* ctx, const uint64_t* keys, const uint64_t* co
  * them; a mismatch is detected at collect time: VC_ERR_INVALID).  A rank that has not posted within the time bound
  * (vc_peer_set_timeout, else the environment variable VC_PEER_TIMEOUT_MS, else 10 s) turns into VC_ERR_STATE -- the
  * post stays pending and vc_sites_collect_peers may simply be called again -- a rank with more than `cap` records
- * into VC_ERR_NOMEM; neither hangs. */
+ * gets VC_ERR_NOMEM from vc_sites_post_peers before anything is stored; neither hangs. */
 int vc_peer_create(vc_ctx* ctx, int world, int rank, int64_t cap, void* handle_out);
 int vc_peer_open(vc_ctx* ctx, const void* handles);
 int vc_peer_open_ptrs(vc_ctx* ctx, void* const* bases);

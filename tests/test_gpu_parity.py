@@ -424,10 +424,8 @@ def test_peer_exchange_errors_do_not_hang(ctx_factory):
     with pytest.raises(api.VoxcoreError, match="not mapped"):
         a.sites_post_peers()  # nothing is ever stored into a buffer laid out differently
     a, b = pair(16)
-    a.sites_post_peers()
-    b.sites_post_peers()
     with pytest.raises(api.VoxcoreError, match="capacity"):
-        a.sites_collect_peers()
+        a.sites_post_peers()  # nothing is stored beyond a region: the rank that overflows says so before it posts
     with pytest.raises(api.VoxcoreError, match="no peer group"):
         ctx_factory().sites_post_peers()
 

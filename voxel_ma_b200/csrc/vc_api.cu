@@ -352,7 +352,7 @@ extern "C"
             pk = dk.as<u64>();
             pc = dc.as<u64>();
         }
-        int s = st_finalize_sites(c, pk, pc, n, true);
+        int s = st_finalize_sites(c, pk, pc, n, VC_SITES_SORT);
         cudaStreamSynchronize(c->stream);
         dk.release();
         dc.release();
@@ -367,7 +367,7 @@ extern "C"
         if (c->z0 != 0 || c->z1 != c->nz)
             return vc_fail(c, VC_ERR_STATE, "vc_extract_sites: slab contexts use vc_sites_detect_local / export / import_global");
         VC_TRY(st_detect_sites(c));
-        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, VC_SITES_SORT));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (nsites)
             *nsites = c->nsites;
@@ -423,7 +423,7 @@ extern "C"
             VC_CUDA(c, dc.ensure((size_t)(n + 1) * 8));
             if (n)
                 VC_CUDA(c, cudaMemcpyAsync(dc.p, corners.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-            int s = st_finalize_sites(c, nullptr, dc.as<u64>(), n, false);
+            int s = st_finalize_sites(c, nullptr, dc.as<u64>(), n, VC_SITES_EXTERNAL);
             cudaStreamSynchronize(c->stream);
             dc.release();
             if (s != VC_OK && s != VC_ERR_UNSUPPORTED) // more sites than the dense path's id fields hold: the cell list has no limit
@@ -542,7 +542,7 @@ extern "C"
         if (c->have_vol || !c->have_inside) // flags from vc_classify_mesh / the f64 upload stand in for a volume
             VC_TRY(st_classify(c));
         VC_TRY(st_detect_sites(c));
-        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, VC_SITES_SORT));
         VC_TRY(st_closest_measures_pipelined(c, true));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (nsites)
@@ -717,7 +717,7 @@ extern "C"
         };
         VC_TRY(d2h_after(inside, c->inside.p, nv));
         VC_TRY(st_detect_sites(c));
-        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+        VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, VC_SITES_SORT));
         VC_TRY(st_closest_measures_pipelined(c, radius != nullptr));
         VC_TRY(d2h_after(id, c->id.p, nv * 4));
         VC_TRY(d2h_after(d2x4, c->d2.p, nv * 4));

@@ -482,7 +482,7 @@ extern "C"
             return vc_fail(c, VC_ERR_NOMEM, "vc_run_dense_host_compact: capacity below the inside count (returned in n_inside)");
         }
         if (c->peer_world < 2)
-            VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, true));
+            VC_TRY(st_finalize_sites(c, c->cand_key.as<u64>(), c->cand_corner.as<u64>(), c->ncand, VC_SITES_SORT));
         mark(3, c->stream);
         host_mark(2);
         VC_TRY(compact_alloc(c, n, true));

@@ -205,11 +205,16 @@ int st_classify_begin(vc_ctx* c);
 int st_classify_planes(vc_ctx* c, int za, int zb);
 int vc_exclusive_scan_u32(vc_ctx* c, u32* a, int64_t len);
 int st_detect_sites(vc_ctx* c);
-int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter);
 void vc_peer_release(vc_ctx* c);
 extern "C" int vc_sites_post_peers(vc_ctx* c);
 extern "C" int vc_sites_collect_peers(vc_ctx* c, int64_t* n_all);
-int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key);
+enum
+{
+    VC_SITES_EXTERNAL = 0,
+    VC_SITES_SORT = 1,
+    VC_SITES_PRESORTED = 2
+};
+int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, int mode);
 int st_closest_lattice(vc_ctx* c);
 int st_measures(vc_ctx* c, bool want_radius);
 // the two stages above for the whole slab, z chunk by z chunk on the worker streams
@@ -239,3 +244,4 @@ int st_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n
 
 // radix sort of (u64 key, u32 value) pairs on bits [0,nbits); result pointers returned
 int vc_radix_sort_pairs(vc_ctx* c, int64_t n, int nbits, u64** keys_io, u32** vals_io);
+int vc_sort_records_by_key(vc_ctx* c, const u64* keys_dev, int64_t n, u64** keys_io, u32** vals_io);

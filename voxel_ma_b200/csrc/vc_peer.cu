@@ -2,13 +2,16 @@
 //
 // Every rank (one process per GPU, one z-slab each) needs the UNION of the boundary-sample records
 // (first-encounter key, corner) of all slabs, because site ids are ranks in the global x-major scan
-// order (src/surfacing.cpp:240-285).  Instead of "detect -> count -> host -> all-gather -> host", the
-// detection kernel itself stores each record into the receive buffer of every rank over NVLink
-// (k_detect_sites<2>, vc_sites.cu), then one warp posts (sequence number, count) into every rank's
-// header with a system-scope release store.  A rank collects by spinning (acquire loads, bounded) on
-// its OWN header lines until all ranks have posted the current sequence number, packs the regions
-// into one contiguous record list and runs the same sort every other rank runs.  One host
-// synchronisation per exchange (the total count sizes the sort launches); no collective library on
+// order (src/surfacing.cpp:240-285).  Round 2: the numbering itself is distributed.  A rank detects the
+// records of its own corner planes, sorts THEM by key (1/world of the records), and one kernel stores the
+// sorted run into the receive buffer of every rank over NVLink (coalesced 8-byte stores straight into peer
+// memory); one warp then posts (sequence number, count) into every rank's header with a system-scope
+// release store.  A rank collects by spinning (acquire loads, bounded in time) on its OWN header lines
+// until all ranks have posted the current sequence number; the id of a record is then its position in
+// the merge of the world sorted runs = its index in its own run + the number of smaller keys in every
+// other run (keys are unique: a corner plane belongs to one slab), found per record by binary searches
+// that a warp narrows for its 32 consecutive records (k_merge_rank) -- no rank ever sorts the union
+// (round 1 did: 0.47 ms per step for 2.7e6 records, replicated on every GPU).  No collective library on
 // the data path -- torch.distributed only carries the 64-byte IPC handles once, at set-up.
 //
 // Receive buffer of a rank (u64 units), double-buffered on the parity of the sequence number so a
@@ -40,12 +43,11 @@ struct VcPeerHdr
 };
 
 // one warp: lane p tells rank p how many records this rank wrote (after they are visible system-wide)
-__global__ void k_peer_post(VcPeerHdr hdr, int world, const u64* __restrict__ counter, u64 seq, u64 cap)
+__global__ void k_peer_post(VcPeerHdr hdr, int world, u64 n, u64 seq, u64 cap)
 {
     const int p = threadIdx.x;
     if (p >= world)
         return;
-    const u64 n = *counter;
     __threadfence_system();
     u64* line = hdr.line[p];
     line[1] = n;
@@ -119,18 +121,82 @@ __global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, 
     }
 }
 
-// records of all regions -> one contiguous list: out[0 .. total) keys, out[total_cap ..) corners
+// this rank's sorted run -> the region (parity, my rank) of every rank's receive buffer: keys[0, n) | corners[cap, cap + n)
 __global__ void __launch_bounds__(256)
-    k_peer_pack(const u64* __restrict__ rec, int world, u64 cap, const u64* __restrict__ off, u64* __restrict__ keys,
-                u64* __restrict__ corners)
+    k_peer_store_run(const u64* __restrict__ ksorted, const u32* __restrict__ order, const u64* __restrict__ corners, u64 n, VcPeerDst dst)
 {
-    const int p = blockIdx.y;
-    const u64 n = off[p + 1] - off[p];
-    const u64* src = rec + (size_t)p * 2ull * cap;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
     {
-        keys[off[p] + i] = __ldcg(src + i); // L2 is where the peers' stores land; never a stale L1 line
-        corners[off[p] + i] = __ldcg(src + cap + i);
+        const u64 k = ksorted[i], pc = corners[order[i]];
+        for (int p = 0; p < dst.world; ++p)
+        {
+            dst.rec[p][i] = k;
+            dst.rec[p][dst.cap + i] = pc;
+        }
+    }
+    __threadfence_system(); // the records are in the peers' memory before the count is posted
+}
+
+__device__ __forceinline__ u64 peer_lower_bound(const u64* __restrict__ k, u64 lo, u64 hi, u64 key)
+{ // first index in [lo, hi) whose key is >= `key`; __ldcg: L2 is where the peers' stores land, never a stale L1 line
+    while (lo < hi)
+    {
+        const u64 mid = (lo + hi) >> 1;
+        if (__ldcg(k + mid) < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// id of a record = its index in its own run + the number of smaller keys in every other run.  One warp takes 32
+// consecutive records of one run: lane q brackets the block's first key in run q and lane 16 + q its last key (two
+// full binary searches per other run, done by different lanes at once), then every lane searches only inside those
+// brackets -- consecutive keys of a run are close in the other runs as well.  Writes the merged tables in id order.
+__global__ void __launch_bounds__(256)
+    k_merge_rank(const u64* __restrict__ rec, int world, u64 cap, const u64* __restrict__ off, u64* __restrict__ keys_out,
+                 u64* __restrict__ corners_out)
+{
+    const int lane = threadIdx.x & 31;
+    u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // block of 32 records, numbered run after run
+    int p = 0;
+    u64 np = 0;
+    for (; p < world; ++p)
+    {
+        np = off[p + 1] - off[p];
+        const u64 nb = (np + 31) >> 5;
+        if (w < nb)
+            break;
+        w -= nb;
+    }
+    if (p >= world)
+        return;
+    const u64* kp = rec + (size_t)p * 2ull * cap;
+    const u64 i0 = w * 32, i = i0 + lane;
+    const bool valid = i < np;
+    const u64 K = valid ? __ldcg(kp + i) : ~0ull;
+    const u64 last = np - 1 - i0 < 31 ? np - 1 - i0 : 31;
+    const u64 K0 = __shfl_sync(0xffffffffu, K, 0), KL = __shfl_sync(0xffffffffu, K, (int)last);
+    const int q = lane & 15;
+    u64 bracket = 0;
+    if (q < world && q != p)
+    {
+        const u64* kq = rec + (size_t)q * 2ull * cap;
+        bracket = peer_lower_bound(kq, 0, off[q + 1] - off[q], lane < 16 ? K0 : KL);
+    }
+    u64 below = 0;
+    for (int r = 0; r < world; ++r)
+    {
+        const u64 lo = __shfl_sync(0xffffffffu, bracket, r), hi = __shfl_sync(0xffffffffu, bracket, 16 + r);
+        if (r != p && valid)
+            below += peer_lower_bound(rec + (size_t)r * 2ull * cap, lo, hi, K);
+    }
+    if (valid)
+    {
+        const u64 gid = i + below;
+        keys_out[gid] = K;
+        corners_out[gid] = __ldcg(kp + cap + i);
     }
 }
 
@@ -294,9 +360,27 @@ extern "C"
             dst.rec[p] = base + peer_rec_off(c->peer_world, c->peer_cap, parity, c->peer_rank);
             hdr.line[p] = base + peer_hdr_off(parity, c->peer_rank);
         }
-        u64* counter = c->scratch.as<u64>() + 2;
-        VC_TRY(st_detect_sites_to_peers(c, dst, counter));
-        VC_LAUNCH(c, "peer_post", k_peer_post, 1, 32, 0, hdr, c->peer_world, counter, seq, (u64)c->peer_cap);
+        // the records of this slab's corner planes, sorted by key HERE (1/world of the union) ...
+        VC_TRY(st_detect_sites(c));
+        const int64_t n = c->ncand;
+        if (n > c->peer_cap)
+            return vc_fail(c, VC_ERR_NOMEM, "vc_sites_post_peers: this rank produced more site records than the capacity given to "
+                                            "vc_peer_create");
+        VC_CUDA(c, c->sk0.ensure((size_t)(n + 1) * 8));
+        VC_CUDA(c, c->sk1.ensure((size_t)(n + 1) * 8));
+        VC_CUDA(c, c->sv0.ensure((size_t)(n + 1) * 4));
+        VC_CUDA(c, c->sv1.ensure((size_t)(n + 1) * 4));
+        u64* k = c->sk0.as<u64>();
+        u32* v = c->sv0.as<u32>();
+        if (n > 0)
+        {
+            VC_TRY(vc_sort_records_by_key(c, c->cand_key.as<u64>(), n, &k, &v));
+            // ... and stored as one sorted run into every rank's receive region over NVLink
+            unsigned blocks = vc_blocks((size_t)n, 256);
+            blocks = blocks > (unsigned)c->sm_count * 8 ? (unsigned)c->sm_count * 8 : blocks;
+            VC_LAUNCH(c, "peer_store_run", k_peer_store_run, blocks, 256, 0, k, v, c->cand_corner.as<u64>(), (u64)n, dst);
+        }
+        VC_LAUNCH(c, "peer_post", k_peer_post, 1, 32, 0, hdr, c->peer_world, (u64)n, seq, (u64)c->peer_cap);
         VC_CUDA(c, cudaGetLastError());
         c->peer_seq = seq;
         c->peer_posted = true;
@@ -319,10 +403,6 @@ extern "C"
                   (u64)c->peer_cap, (u64)c->peer_timeout_ms * 1000000ull, off, res);
         u64* keys = c->peer_all.as<u64>();
         u64* corners = keys + (size_t)world * (size_t)c->peer_cap;
-        unsigned bx = vc_blocks((size_t)c->peer_cap, 256);
-        bx = bx > 1024u ? 1024u : bx;
-        VC_LAUNCH(c, "peer_pack", k_peer_pack, dim3(bx, world), 256, 0, base + peer_rec_off(world, c->peer_cap, parity, 0), world,
-                  (u64)c->peer_cap, off, keys, corners);
         u64* h = (u64*)c->pinned;
         VC_CUDA(c, cudaMemcpyAsync(h, res, 16, cudaMemcpyDeviceToHost, c->stream));
         VC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -339,6 +419,12 @@ extern "C"
         const int64_t n = (int64_t)h[0];
         if (n_all)
             *n_all = n;
-        return st_finalize_sites(c, keys, corners, n, true);
+        if (n > 0)
+        { // merge the sorted runs by ranking: every record straight to its id
+            const size_t warps = (size_t)(n + 31) / 32 + (size_t)world;
+            VC_LAUNCH(c, "merge_rank", k_merge_rank, vc_blocks(warps * 32, 256), 256, 0, base + peer_rec_off(world, c->peer_cap, parity, 0),
+                      world, (u64)c->peer_cap, off, keys, corners);
+        }
+        return st_finalize_sites(c, keys, corners, n, VC_SITES_PRESORTED);
     }
 }

@@ -273,11 +273,9 @@ int st_upload_f64_zfast(vc_ctx* c, const double* vol)
 // Warp-aggregated append; the order of the appended records does not matter because the keys are
 // unique and sorted afterwards.
 // =============================================================================================
-// MODE 0: count only.  MODE 1: append (key, corner) records to keys[] / corners[].  MODE 2: append every
-// record to the receive region of EVERY rank of the slab group (vc_peer.cu): plain 8-byte stores
-// into peer memory over NVLink, no count pass -- a region has a fixed capacity and the counter tells
-// the receivers afterwards how many records (or that it overflowed).
-#define DS_STAGE 128 // records a warp stages per round (2 KB of shared memory per warp)
+// MODE 0: count only.  MODE 1: append (key, corner) records to keys[] / corners[] (peers.cap carries their capacity).
+// (Round 1 had a MODE 2 that stored every record straight into every rank's receive region; the exchange now posts
+// a locally SORTED run instead, vc_peer.cu: k_peer_store_run.)
 template <int MODE>
 __global__ void __launch_bounds__(256)
     k_detect_sites(const u32* __restrict__ bits, int wr, int nx, int ny, int nz, int zlo, int czb, int cze,
@@ -362,60 +360,6 @@ __global__ void __launch_bounds__(256)
         }
         return;
     }
-    // The warp's records are staged in shared memory in the order of their reserved slots and then written out by the
-    // whole warp, lane i taking record i, i + 32, ...: every store instruction covers 256 contiguous bytes -- what the
-    // NVLink path to a peer's memory wants (one 8-byte store per record and peer is a transaction each: 0.58 ms for
-    // 5e5 records to 8 peers, measured).  Rounds of DS_STAGE records; a warp rarely has more.
-    __shared__ u64 stage[MODE == 2 ? 8 : 1][2][MODE == 2 ? DS_STAGE : 1];
-    const int warp = threadIdx.x >> 5;
-    int mine = incl - cnt; // slot (within the warp's batch) of this lane's next record
-    for (int r0 = 0; r0 < warp_total; r0 += DS_STAGE)
-    {
-        while (site && mine < r0 + DS_STAGE)
-        {
-            const int b = __ffs(site) - 1;
-            site &= site - 1;
-            const int cx = 32 * w + b;
-            u32 occ = 0, inb = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            { // voxel (cx-1+a, cy-1+(k>>1), cz-1+(k&1)) -> bit a*4 + k of occ / inb
-                const u32 lo = b > 0 ? (cur[k] >> (b - 1)) & 1u : prv[k] >> 31; // x = cx-1
-                const u32 hi = (cur[k] >> b) & 1u;                              // x = cx
-                occ |= (lo << k) | (hi << (4 + k));
-                const u32 rin = (rows_in >> k) & 1u;
-                inb |= ((cx >= 1 ? rin : 0u) << k) | ((cx < nx ? rin : 0u) << (4 + k));
-            }
-            stage[warp][0][mine - r0] = vc_site_key(occ, inb, cx, cy, cz, ny, nz);
-            stage[warp][1][mine - r0] = vc_pack_corner(cx, cy, cz);
-            ++mine;
-        }
-        __syncwarp();
-        const int nrec = min(DS_STAGE, warp_total - r0);
-        for (int i = lane; i < nrec; i += 32)
-        {
-            const u64 key = stage[warp][0][i], corner = stage[warp][1][i];
-            const u64 pos = base + (u64)(r0 + i);
-            if (MODE == 1)
-            {
-                keys[pos] = key;
-                corners[pos] = corner;
-            }
-            else if (pos < peers.cap)
-            {
-#pragma unroll
-                for (int p = 0; p < VC_MAX_PEERS; ++p)
-                    if (p < peers.world)
-                    {
-                        peers.rec[p][pos] = key;
-                        peers.rec[p][peers.cap + pos] = corner;
-                    }
-            }
-        }
-        __syncwarp();
-    }
-    if (MODE == 2)
-        __threadfence_system(); // the records are in the peers' memory before the count is posted (vc_peer.cu)
 }
 
 int st_detect_sites(vc_ctx* c)
@@ -459,24 +403,6 @@ int st_detect_sites(vc_ctx* c)
         cap = (size_t)n; // the counter counted everything: the second attempt fits exactly
     }
     return vc_fail(c, VC_ERR_STATE, "site detection: record count changed between two passes over the same flags");
-}
-
-// Site detection of this slab's corner planes written straight into every rank's receive region
-// (one pass: the regions have a fixed capacity, so nothing has to be counted first).  `counter`
-// (device, zeroed here) ends up holding the number of records this rank produced.
-int st_detect_sites_to_peers(vc_ctx* c, const VcPeerDst& dst, u64* counter)
-{
-    if (!c->have_inside)
-        return vc_fail(c, VC_ERR_STATE, "site extraction needs vc_classify_grid first");
-    int czb = c->z0, cze = (c->z1 == c->nz) ? c->nz + 1 : c->z1;
-    if (c->zlo > (czb > 0 ? czb - 1 : 0) || c->zhi < (cze - 1 < c->nz ? cze : c->nz))
-        return vc_fail(c, VC_ERR_STATE, "resident voxel planes do not cover the slab's corner planes");
-    size_t total = (size_t)c->wr * (c->ny + 1) * (size_t)(cze - czb);
-    VC_CUDA(c, cudaMemsetAsync(counter, 0, 8, c->stream));
-    VC_LAUNCH(c, "detect_sites_emit_peers", k_detect_sites<2>, vc_blocks(total, 256), 256, 0, c->bits.as<u32>(), c->wr, c->nx,
-              c->ny, c->nz, c->zlo, czb, cze, nullptr, nullptr, counter, dst);
-    VC_CUDA(c, cudaGetLastError());
-    return VC_OK;
 }
 
 // =============================================================================================
@@ -1171,8 +1097,22 @@ static int bits_for(u64 maxval)
     return b;
 }
 
-int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, bool sort_by_key)
+// (first-encounter key, index) pairs of n records in key order: *keys_io / *vals_io (buffers sk0/sk1, sv0/sv1 of the
+// ctx, which the caller has sized) come back pointing at the sorted keys and at the permutation
+int vc_sort_records_by_key(vc_ctx* c, const u64* keys_dev, int64_t n, u64** keys_io, u32** vals_io)
 {
+    VC_LAUNCH(c, "sites_iota", k_iota_copy, vc_blocks((size_t)n, 256), 256, 0, keys_dev, *keys_io, *vals_io, n);
+    const u64 maxkey = ((u64)c->nx * c->ny * c->nz) * 24ull;
+    return vc_radix_sort_pairs(c, n, bits_for(maxkey), keys_io, vals_io);
+}
+
+// mode: VC_SITES_EXTERNAL  ids = the order given (external sample set; repeated points are detected),
+//       VC_SITES_SORT      ids = rank of the first-encounter key (records in any order),
+//       VC_SITES_PRESORTED the records already ARE in key order (the merged runs of the peer exchange): no sort
+int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, int64_t n, int mode)
+{
+    const bool sort_by_key = mode == VC_SITES_SORT;
+    const bool external = mode == VC_SITES_EXTERNAL;
     const int nlines = (c->nx + 1) * (c->ny + 1);
     if (n > (int64_t)VC_MAX_SITE_ID + 1)
         return vc_fail(c, VC_ERR_UNSUPPORTED, "more than 2^25 sites: ids no longer fit the packed 25-bit id fields of the dense path");
@@ -1211,6 +1151,8 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
         order = v;
         ksorted = k;
     }
+    if (mode == VC_SITES_PRESORTED)
+        ksorted = keys_dev;
     // key2/val2 go to the buffers the first sort is NOT currently holding its result in
     u64* k2 = (k == c->sk0.as<u64>()) ? c->sk1.as<u64>() : c->sk0.as<u64>();
     u32* v2 = (v == c->sv0.as<u32>()) ? c->sv1.as<u32>() : c->sv0.as<u32>();
@@ -1225,7 +1167,7 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
         VC_LAUNCH(c, "line_entries", k_line_entries, blocks, 256, 0, k2, v2, c->line_ent.as<u64>(), n, c->nz);
         VC_LAUNCH(c, "line_ptr", k_line_ptr, vc_blocks((size_t)nlines + 1, 256), 256, 0, k2, n, nlines, c->nz,
                   c->line_ptr.as<int>());
-        if (!sort_by_key)
+        if (external)
         {
             VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
             VC_LAUNCH(c, "count_dups", k_count_dups, blocks, 256, 0, k2, n, counter);
@@ -1248,16 +1190,16 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
         VC_CUDA(c, cudaMemcpyAsync(cursor, ptr, (size_t)(nlines + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
         VC_LAUNCH(c, "line_fill", k_line_fill, blocks, 256, 0, c->site_corner.as<u64>(), n, CY, cursor, k2);
         VC_LAUNCH(c, "line_sort", k_line_sort_short, vc_blocks((size_t)nlines, 256), 256, 0, c->line_ptr.as<int>(), nlines, k2,
-                  c->line_ent.as<u64>(), long_lines + 1, long_lines, sort_by_key ? (u64*)nullptr : counter);
+                  c->line_ent.as<u64>(), long_lines + 1, long_lines, external ? counter : (u64*)nullptr);
         VC_LAUNCH(c, "line_sort", k_line_sort_long, c->sm_count * 2, 256, 0, c->line_ptr.as<int>(), k2, c->line_ent.as<u64>(),
-                  long_lines + 1, long_lines, sort_by_key ? (u64*)nullptr : counter);
+                  long_lines + 1, long_lines, external ? counter : (u64*)nullptr);
     }
     {
         const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
         VC_LAUNCH(c, "line_mask", k_line_mask, vc_blocks((size_t)CY * nw, 256), 256, 0, c->line_ptr.as<int>(), CX, CY, nw,
                   c->colmask.as<u32>());
     }
-    if (!sort_by_key)
+    if (external)
     { // external set: duplicates on the lattice would need the lowest-id rule inside a list entry
         u64 d = 0;
         VC_CUDA(c, cudaMemcpyAsync(&d, counter, 8, cudaMemcpyDeviceToHost, c->stream));
