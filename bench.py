@@ -365,19 +365,23 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
     z0, z1 = slabs.slab_bounds(nz, world, rank)
     lo, hi = slabs.resident_planes(z0, z1, nz)
     planes = make_planes(fam, grid, lo, hi)
-    if world > 1 and args.balance > 0:
-        # EXPERIMENTAL (off by default): slab heights from a per-plane work estimate 1 + c * inside fraction
-        # (slabs.balanced_bounds) instead of equal heights; every rank counts its own planes, the counts are gathered
+    heights = "equal"
+    if world > 1 and (args.balance > 0 or args.align > 1):
+        # slab heights from a per-plane work estimate 1 + c * inside fraction (the measures of a plane cost more where
+        # it cuts solids), cuts snapped so that a slab's planes + its halo plane fill whole warps of pass X
+        # (slabs.aligned_bounds); every rank counts its own planes, the counts are gathered
         frac = (planes[z0 - lo:z1 - lo] > 0).reshape(z1 - z0, -1).mean(axis=1)
         per = [None] * world
         dist.all_gather_object(per, (z0, frac.astype(np.float64)))
         full = np.zeros(nz)
         for zz, f in per:
             full[zz:zz + len(f)] = f
-        z0, z1 = slabs.balanced_bounds(1.0 + args.balance * full, world)[rank]
+        w = 1.0 + max(args.balance, 0.0) * full
+        z0, z1 = (slabs.aligned_bounds(w, world, args.align) if args.align > 1 else slabs.balanced_bounds(w, world))[rank]
         lo, hi = slabs.resident_planes(z0, z1, nz)
         planes = make_planes(fam, grid, lo, hi)
-        print(f"[rank {rank}] balanced slab [{z0},{z1}) = {z1 - z0} planes", file=sys.stderr)
+        heights = f"weights 1 + {args.balance} x inside fraction of the plane, cuts aligned to {args.align} planes incl. the halo plane"
+        print(f"[rank {rank}] slab [{z0},{z1}) = {z1 - z0} planes", file=sys.stderr)
     ctx = api.Context(local)
     ctx.set_grid(nx, ny, nz, z0, z1)
     # pinned staging of the slab (the e2e leg copies from here every step)
@@ -631,7 +635,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64/f32",
             "data": "synthetic",
             "config": {"workload": wname, "sites": state["nsites"], "z_slabs": world,
-                       "slab_heights": "equal" if args.balance <= 0 else f"balanced (1 + {args.balance} x inside fraction)",
+                       "slab_heights": heights,
                        "vertices_per_gpu": nv_local,
                        "exchange": ("none (one slab)" if world == 1 else
                                     "peer memory: detection kernel stores records into every rank over NVLink (vc_peer.cu)"
@@ -746,8 +750,10 @@ def main():
                     "512x512x1024 / 512x1024x1024 / 1024^3 at N=2/4/8)")
     ap.add_argument("--no-at512", action="store_true", help="N=1: skip the secondary twist512 measurement")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
-    ap.add_argument("--balance", type=float, default=0.0, help="EXPERIMENTAL, N>1: weight c of the per-plane inside fraction in the "
-                    "slab-height estimate 1 + c*fraction (0 = equal heights, the default)")
+    ap.add_argument("--balance", type=float, default=0.0, help="N>1: weight c of the per-plane inside fraction in the slab-height "
+                    "estimate 1 + c*fraction (0 = equal weights)")
+    ap.add_argument("--align", type=int, default=32, help="N>1: snap the slab cuts so that planes + halo plane of a slab are a multiple "
+                    "of this many planes (32 = the planes one warp of pass X holds; 1 = no snapping)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
     ap.add_argument("--exchange", default="peers", choices=["peers", "nccl"],
                     help="N>1: how the site records travel between ranks (peer-memory kernel stores, or NCCL all-gather)")

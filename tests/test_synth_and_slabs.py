@@ -75,3 +75,19 @@ def test_balanced_bounds():
     assert {z1 - z0 for z0, z1 in b} == {125}
     with pytest.raises(ValueError):
         slabs.balanced_bounds(np.ones(3), 4)
+
+
+def test_aligned_bounds():
+    """slab cuts snapped so that planes + halo plane of every slab below the top fill whole 32-plane warps of pass X"""
+    from voxel_ma_b200 import slabs
+    rng = np.random.default_rng(5)
+    for nz, world in ((1024, 8), (1024, 4), (1024, 2), (2048, 8), (512, 8), (700, 3)):
+        w = 1.0 + 3.0 * rng.random(nz)
+        b = slabs.aligned_bounds(w, world, 32)
+        assert b[0][0] == 0 and b[-1][1] == nz and all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(z1 > z0 for z0, z1 in b)
+        assert all((z1 - z0 + 1) % 32 == 0 for z0, z1 in b[:-1])
+    assert [z1 - z0 for z0, z1 in slabs.aligned_bounds(np.ones(1024), 8, 32)] == [127] * 7 + [135]
+    # too thin for aligned slabs: the balanced cuts are kept
+    assert slabs.aligned_bounds(np.ones(40), 3, 32) == slabs.balanced_bounds(np.ones(40), 3)
+    assert slabs.aligned_bounds(np.ones(64), 1, 32) == [(0, 64)]

@@ -37,6 +37,8 @@ for s in range(nslabs):
 scratch.close()
 keys, corners = np.concatenate(keys), np.concatenate(corners)
 z0, z1 = k * h, (k + 1) * h
+if os.environ.get("VC_SLAB"):  # explicit planes "z0,z1" instead of slab k
+    z0, z1 = (int(v) for v in os.environ["VC_SLAB"].split(","))
 lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
 c = api.Context(0)
 c.set_grid(nx, ny, nz, z0, z1)

@@ -506,18 +506,20 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
     }
     const int nplanes_all = c->zc - c->z0;
     const int nw = c->profiling ? 0 : c->nworkers;
-    // chunk height: a multiple of 32 planes (pass X puts 32 planes in a warp) with >= 32k lines per launch so that
-    // a chunk's kernels are efficient on their own (64 planes at 512^2), VC_ZCHUNK overrides; one chunk when profiling
+    // chunk height: a multiple of 32 planes (pass X puts 32 planes in a warp), >= 64 planes and >= 32k lines per
+    // launch so that a chunk's kernels are efficient on their own, and no more chunks than about one per worker stream;
+    // VC_ZCHUNK overrides.  Fewer than three chunks do not pay (measured: two are slower than one -- a 129-plane slab of
+    // a 1024^2 grid runs 4.11 ms as one chunk, 4.30 as four, 4.40 as two), so a thin slab is one chunk.
     int zchunk = c->zchunk;
     if (zchunk <= 0)
     {
         const int side = c->nx < c->ny ? c->nx : c->ny;
         zchunk = (32768 + side - 1) / side;
-        zchunk = ((zchunk < 32 ? 32 : zchunk) + 31) / 32 * 32;
-        // ... and no more chunks than about one per worker stream: with many more (1024^3 on one GPU: 32) the
-        // launch count costs more than the overlap gives
+        zchunk = ((zchunk < 64 ? 64 : zchunk) + 31) / 32 * 32;
         const int per_worker = ((nplanes_all + (nw > 0 ? nw : 1) - 1) / (nw > 0 ? nw : 1) + 31) / 32 * 32;
         zchunk = zchunk < per_worker ? per_worker : zchunk;
+        if (nplanes_all / zchunk < 3)
+            zchunk = nplanes_all;
     }
     if (!nw || zchunk > nplanes_all)
         zchunk = nplanes_all;

@@ -46,6 +46,30 @@ def balanced_bounds(weights, world: int) -> list[tuple[int, int]]:
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def aligned_bounds(weights, world: int, align: int = 32) -> list[tuple[int, int]]:
+    """balanced_bounds with the cuts snapped so that every slab below the top one has  height + 1 = 0 (mod align):
+    pass X of the transform puts `align` = 32 consecutive planes of a slab into one warp, and a slab that is not the
+    top one also transforms one halo plane -- 128 + 1 planes would cost a fifth group of warps for that one plane,
+    127 + 1 planes cost none.  The top slab (no halo plane) takes whatever remains.  Falls back to balanced_bounds
+    when the grid is too thin for aligned slabs."""
+    nz = len(weights)
+    base = balanced_bounds(weights, world)
+    if world == 1 or nz < world * align:
+        return base
+    cuts = [0]
+    for r in range(1, world):
+        target = base[r][0]
+        # heights h with (h + 1) % align == 0 around the balanced cut: the nearest that leaves room for the slabs above
+        h = max(align - 1, int(round((target - cuts[-1] + 1) / align)) * align - 1)
+        while cuts[-1] + h > nz - (world - r) * (align - 1) and h > align - 1:
+            h -= align
+        cuts.append(cuts[-1] + h)
+    cuts.append(nz)
+    if any(cuts[i + 1] <= cuts[i] for i in range(world)):
+        return base
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def resident_planes(z0: int, z1: int, nz: int) -> tuple[int, int]:
     """Voxel planes a slab needs resident: its own planes plus one halo plane on each interior side
     (the lower one feeds the slab's first corner plane, the upper one the cells that reach up)."""
