@@ -234,6 +234,21 @@ int vc_download(vc_ctx* ctx, int which, void* dst);
 int vc_download_planes(vc_ctx* ctx, int which, int za, int zb, void* dst);
 /* device pointer of a result array (valid until the next stage call / destroy) */
 void* vc_device_ptr(vc_ctx* ctx, int which);
+/* ---- next row 8(f-4): the medial complex of the dense product, read off the id grid ----------------------
+ * Replaces (for the DENSE product only) the TetGen Voronoi construction + inside filter of
+ * src/highlevelalgo.cpp:503-529 / src/voroinfo.cpp:128-139,624-729: a grid edge (v, v + e_axis) whose end
+ * vertices have different closest sites is crossed by the Voronoi face of those two sites; its dual is the quad
+ * spanned by the centres of the 4 grid cubes around the edge.  A quad is emitted iff those 4 cubes exist and
+ * all their vertices are inside (include/voroinfo_imp.h:26-34), so the quads form a closed cubical 2-complex in
+ * the form cellcomplex::finalize / CellComplexThinning take (src/cellcomplex.cpp:364-491, src/ccthin.cpp:201-424).
+ * Needs vc_classify_grid + closest sites (vc_closest_grid / vc_run_dense).  Records in ascending (z, y, x, axis):
+ *   anchor[i]  linear index of v inside this ctx's owned planes,  axis[i] in {0,1,2} = +x,+y,+z,
+ *   site_a/b   closest-site ids of v and v + e_axis,  lambda[i] = lambdaForFace(site_a, site_b) (float32).
+ * The complex differs from TetGen's (unit quads instead of general polygons): compared on statistics only. */
+int vc_medial_quads_count(vc_ctx* ctx, int64_t* nquads);
+int vc_medial_quads(vc_ctx* ctx, int64_t cap, uint32_t* anchor, uint8_t* axis, int32_t* site_a, int32_t* site_b, float* lambda,
+                    int64_t* nquads);
+
 /* Host-buffer end-to-end step: H2D of the float32 volume, the hot path, D2H of every non-NULL
  * output, copies and kernels overlapped plane-chunk by plane-chunk.  Pinned buffers
  * (vc_host_alloc) reach PCIe speed. */

@@ -72,6 +72,9 @@ def oracle():
         lib.orc_closest_grid.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _i32p, C.c_void_p, C.c_void_p]
         lib.orc_closest_grid_sample.argtypes = [_f32p, C.c_int64, _i32p, C.c_int64, _i32p, _u32p]
+        lib.orc_medial_quads.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_medial_quads.restype = C.c_int64
         lib.orc_face_lambda.argtypes = [_f32p, _i32p, C.c_int64, _f32p]
         lib.orc_vertex_radii.argtypes = [_f32p, _f32p, C.c_int64, _i32p, _f32p]
         lib.orc_segment_max.argtypes = [_i32p, _i32p, C.c_int64, _f32p, C.c_void_p, _f32p]
@@ -246,6 +249,22 @@ def closest_grid_sample(sites_xyz, q_xyz):
     d2 = np.empty(len(q), np.uint32)
     oracle().orc_closest_grid_sample(s, len(s), q, len(q), ids, d2)
     return ids, d2
+
+
+def medial_quads(sites_xyz, ids, inside, nx, ny, nz, z0=0, z1=None, zlo=0):
+    """dual quads of the crossing grid edges anchored in planes [z0, z1); ids / inside hold planes [zlo, zlo + len)"""
+    z1 = nz if z1 is None else z1
+    s = np.ascontiguousarray(sites_xyz, np.float32)
+    i = np.ascontiguousarray(ids, np.int32)
+    f = np.ascontiguousarray(inside, np.uint8)
+    zhi = zlo + i.shape[0]
+    n = oracle().orc_medial_quads(s, i, f, nx, ny, nz, zlo, zhi, z0, z1, 0, None, None, None, None, None)
+    m = max(int(n), 1)
+    anchor, axis = np.empty(m, np.uint32), np.empty(m, np.uint8)
+    a, b, lam = np.empty(m, np.int32), np.empty(m, np.int32), np.empty(m, np.float32)
+    oracle().orc_medial_quads(s, i, f, nx, ny, nz, zlo, zhi, z0, z1, m, anchor.ctypes.data, axis.ctypes.data, a.ctypes.data,
+                              b.ctypes.data, lam.ctypes.data)
+    return anchor[:n], axis[:n], a[:n], b[:n], lam[:n]
 
 
 def face_lambda(sites_xyz, site_pairs):

@@ -472,6 +472,56 @@ void orc_cell_measures_grid(const float* sites_xyz, const int32_t* id, const uin
 #undef MAX2
 }
 
+/* ---- next row 8(f-4): dual quads of the crossing grid edges (the medial complex of the dense product) ----------
+ * PARITY UNPINNED for the complex (the reference's complex is TetGen's Voronoi diagram, src/highlevelalgo.cpp:503-529;
+ * this cubical one can only be compared on statistics); the rules are the builder's, stated in
+ * include/voxcore_gpu.h (vc_medial_quads): a grid edge (v, v + e_axis) with different closest sites at its ends gets a
+ * quad iff the 4 cubes around it exist and all their vertices are inside (validity as include/voroinfo_imp.h:26-34);
+ * lambda = lambdaForFace of the two sites (pinned arithmetic, lambda_f above).  Order: z, y, x, axis ascending.
+ * id / inside: planes [zlo, zhi) of the grid with zlo <= z0 - 1 (or 0) and zhi >= z1 + 1 (or nz); anchors are
+ * relative to plane z0.  Returns the number of quads; writes at most cap. */
+int64_t orc_medial_quads(const float* sites_xyz, const int32_t* id, const uint8_t* inside, int nx, int ny, int nz, int zlo,
+                         int zhi, int z0, int z1, int64_t cap, uint32_t* anchor, uint8_t* axis, int32_t* ida, int32_t* idb,
+                         float* lam)
+{
+#define IN(x, y, z) ((x) >= 0 && (x) < nx && (y) >= 0 && (y) < ny && (z) >= zlo && (z) < zhi && (z) >= 0 && (z) < nz && \
+                     inside[(size_t)(x) + (size_t)nx * ((size_t)(y) + (size_t)ny * (size_t)((z) - zlo))])
+#define ID(x, y, z) id[(size_t)(x) + (size_t)nx * ((size_t)(y) + (size_t)ny * (size_t)((z) - zlo))]
+    int64_t n = 0;
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+                for (int a = 0; a < 3; ++a)
+                {
+                    /* the 2 x 3 x 3 block of vertices of the 4 cubes around the edge: 2 along the edge, 3 x 3 across */
+                    int lo[3] = {x - 1, y - 1, z - 1}, hi[3] = {x + 1, y + 1, z + 1};
+                    lo[a] += 1; /* along the edge: the two end vertices only */
+                    int ok = 1;
+                    for (int zz = lo[2]; zz <= hi[2] && ok; ++zz)
+                        for (int yy = lo[1]; yy <= hi[1] && ok; ++yy)
+                            for (int xx = lo[0]; xx <= hi[0] && ok; ++xx)
+                                ok = IN(xx, yy, zz);
+                    if (!ok)
+                        continue;
+                    const int x1 = x + (a == 0), y1 = y + (a == 1), zq = z + (a == 2);
+                    const int32_t i0 = ID(x, y, z), i1 = ID(x1, y1, zq);
+                    if (i0 == i1)
+                        continue;
+                    if (n < cap)
+                    {
+                        anchor[n] = (uint32_t)((size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)(z - z0)));
+                        axis[n] = (uint8_t)a;
+                        ida[n] = i0;
+                        idb[n] = i1;
+                        lam[n] = lambda_f(sites_xyz + 3 * (size_t)i0, sites_xyz + 3 * (size_t)i1);
+                    }
+                    ++n;
+                }
+#undef IN
+#undef ID
+    return n;
+}
+
 /* ---- 1': parity classification of the grid from a closed triangle mesh --------------------------
  * PARITY UNPINNED: the reference has no mesh voxeliser (stage 1'), so there is
  * nothing of the reference to pin this against.  It is pinned instead (tests/test_mesh_classify.py)

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvoxcore_gpu.so")
-SOURCES = ["vc_api.cu", "vc_sites.cu", "vc_edt.cu", "vc_measures.cu", "vc_points.cu", "vc_mesh.cu", "vc_thin.cu", "vc_peer.cu", "vc_compact.cu"]
+SOURCES = ["vc_api.cu", "vc_sites.cu", "vc_edt.cu", "vc_measures.cu", "vc_points.cu", "vc_mesh.cu", "vc_thin.cu", "vc_peer.cu", "vc_compact.cu", "vc_medial.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -77,13 +77,14 @@ DROPIN_CLI = os.path.join(HERE, "host", "_build", "main_voroUtility_gpu")
 
 
 def build_dropin_cli(reference_tree: str = "/root/reference"):
-    """The reference CLI linked against host/dropin/*.cpp + libvoxcore_gpu.so (host/Makefile.dropin).
-    Needs the reference tree and its objects (oracle/_ref/obj, built by oracle/Makefile.ref): possible
-    in the build container only; the binary then travels with the snapshot.  Returns its path or None."""
+    """The reference CLI linked against host/dropin/*.cpp + libvoxcore_gpu.so, and the dense-core tool
+    (host/Makefile.dropin: it compiles the reference's host objects from the reference tree itself, under
+    host/_build).  Needs the reference tree: possible in the build container only; the binaries then travel
+    with the snapshot.  Returns the CLI's path or None."""
     root = os.path.dirname(HERE)
-    if not (os.path.isdir(reference_tree) and os.path.isdir(os.path.join(root, "oracle", "_ref", "obj"))):
+    if not os.path.isdir(reference_tree):
         return DROPIN_CLI if os.path.exists(DROPIN_CLI) else None
-    r = subprocess.run(["make", "-f", os.path.join("voxel_ma_b200", "host", "Makefile.dropin"), f"REF={reference_tree}"],
+    r = subprocess.run(["make", "-j8", "-f", os.path.join("voxel_ma_b200", "host", "Makefile.dropin"), f"REF={reference_tree}"],
                        cwd=root, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"drop-in CLI build failed:\n{r.stdout}\n{r.stderr}")

@@ -148,7 +148,7 @@ extern "C"
                           &c->site_xyz, &c->line_ptr, &c->line_ent, &c->g1, &c->g2, &c->stk, &c->id, &c->d2, &c->edge3,
                           &c->face3, &c->cube, &c->radius, &c->sk0, &c->sk1, &c->sv0, &c->sv1, &c->shist,
                           &c->scratch, &c->cl_ptr, &c->cl_ent, &c->gsites, &c->colmask, &c->line_cur, &c->scan_sums, &c->rowpre, &c->crec,
-                          &c->row_ptr, &c->live_row, &c->row_mask, &c->col_x, &c->col_line, &c->edt_meta};
+                          &c->row_ptr, &c->live_row, &c->row_mask, &c->col_x, &c->col_line, &c->edt_meta, &c->medial_pre};
         for (auto e : c->ev_chunk)
             cudaEventDestroy(e);
         for (auto b : bufs)

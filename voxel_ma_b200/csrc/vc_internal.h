@@ -122,6 +122,7 @@ struct vc_ctx
     // compact product (vc_compact.cu): exclusive prefix of the inside count per bit row of the owned planes,
     // records of the inside vertices; chunk_hook runs after the measures of each z chunk of the pipeline
     DevBuf rowpre, crec;
+    DevBuf medial_pre; // per-row prefix of the dual-quad counts (vc_medial.cu)
     int64_t ninside = -1, ccap = 0;
     std::function<int(int, int)> chunk_hook;
     int compact_mode = 0;             // 0 automatic, 1 dense planes + gather, 2 records computed directly

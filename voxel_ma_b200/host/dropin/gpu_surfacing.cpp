@@ -30,11 +30,15 @@ bool make_resident(const std::shared_ptr<Volume3DScalar>& vol)
         return false;
     const int nx = vol->getSizeX(), ny = vol->getSizeY(), nz = vol->getSizeZ();
     std::vector<double> zfast((size_t)nx * ny * nz);
-    size_t i = 0;
+    const Volume3DScalar* v = vol.get(); // the const accessor: a plain array read, safe from several threads
+#pragma omp parallel for schedule(static)
     for (int x = 0; x < nx; ++x)
+    {
+        size_t i = (size_t)x * ny * nz;
         for (int y = 0; y < ny; ++y)
             for (int z = 0; z < nz; ++z)
-                zfast[i++] = vol->getDataAt(x, y, z);
+                zfast[i++] = v->getDataAt(x, y, z);
+    }
     return s.set_volume(vol.get(), zfast.data(), nx, ny, nz);
 }
 } // namespace vcgpu
