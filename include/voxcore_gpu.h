@@ -234,6 +234,16 @@ int vc_download(vc_ctx* ctx, int which, void* dst);
 int vc_download_planes(vc_ctx* ctx, int which, int za, int zb, void* dst);
 /* device pointer of a result array (valid until the next stage call / destroy) */
 void* vc_device_ptr(vc_ctx* ctx, int which);
+/* ---- stage 3, optional outputs: circumradius and object angle of each cell's closest-point set -----------------
+ * north_star names them next to lambda; the reference only sketches a circumradius in comments
+ * (src/voroinfo.cpp:1441-1443,1475-1479,1526-1530) and has no angle: PARITY UNPINNED, the definition is the builder's
+ * (voxel_ma_b200/csrc/vc_circum.cu; restated in oracle/oracle.c, compared to 1e-12).  Per cell of the 7 anchored at a
+ * vertex (edges +x +y +z, faces xy xz yz, cube; 0 unless all its vertices are inside), in float64, with P = the distinct
+ * closest sites of the cell's vertices and m = the cell's centre:
+ *   circum7[c]  radius of the smallest ball enclosing P;   angle7[c]  max over pairs of angle(p - m, q - m) / 2.
+ * Planes [za, zb) of this ctx's owned planes; outputs [7][zb-za][y][x] doubles, host or device pointers. */
+int vc_cell_circum_angle_grid(vc_ctx* ctx, int za, int zb, double* circum7, double* angle7);
+
 /* ---- next row 8(f-4): the medial complex of the dense product, read off the id grid ----------------------
  * Replaces (for the DENSE product only) the TetGen Voronoi construction + inside filter of
  * src/highlevelalgo.cpp:503-529 / src/voroinfo.cpp:128-139,624-729: a grid edge (v, v + e_axis) whose end

@@ -72,6 +72,7 @@ def oracle():
         lib.orc_closest_grid.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _i32p, C.c_void_p, C.c_void_p]
         lib.orc_closest_grid_sample.argtypes = [_f32p, C.c_int64, _i32p, C.c_int64, _i32p, _u32p]
+        lib.orc_cell_circum_angle_grid.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, _f64p]
         lib.orc_medial_quads.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_medial_quads.restype = C.c_int64
@@ -249,6 +250,16 @@ def closest_grid_sample(sites_xyz, q_xyz):
     d2 = np.empty(len(q), np.uint32)
     oracle().orc_closest_grid_sample(s, len(s), q, len(q), ids, d2)
     return ids, d2
+
+
+def cell_circum_angle_grid(sites_xyz, ids, inside, nx, ny, nz, z0=0, z1=None):
+    """ids / inside hold planes [z0, min(z1+1, nz)); outputs [7][z1-z0][ny][nx] float64 (circumradius, object angle)"""
+    z1 = nz if z1 is None else z1
+    circ = np.empty((7, z1 - z0, ny, nx), np.float64)
+    ang = np.empty_like(circ)
+    oracle().orc_cell_circum_angle_grid(np.ascontiguousarray(sites_xyz, np.float32), np.ascontiguousarray(ids, np.int32),
+                                        np.ascontiguousarray(inside, np.uint8), nx, ny, nz, z0, z1, circ, ang)
+    return circ, ang
 
 
 def medial_quads(sites_xyz, ids, inside, nx, ny, nz, z0=0, z1=None, zlo=0):

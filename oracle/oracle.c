@@ -13,7 +13,8 @@
  * The dense per-cell measure dictionary (orc_cell_measures_grid) has no reference counterpart as
  * an iteration space; its arithmetic (lambdaForFace + max-aggregation +
  * validity) is pinned through the functions above, its iteration space is builder-defined.
- * Circumradius / object angle are not implemented anywhere: "parity unpinned" for those.
+ * Circumradius / object angle (orc_cell_circum_angle_grid) exist nowhere in the reference but in comments:
+ * builder-defined, "parity unpinned".
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC oracle/oracle.c -o oracle/_build/liboracle.so -lm
  * (no -march: no FMA contraction, so float results have one meaning).
@@ -470,6 +471,170 @@ void orc_cell_measures_grid(const float* sites_xyz, const int32_t* id, const uin
             }
 #undef L
 #undef MAX2
+}
+
+/* ---- stage 3 extras: circumradius and object angle of a cell's closest-point set ---------------------------------
+ * PARITY UNPINNED: the reference has neither (a circumradius only in comments, src/voroinfo.cpp:1441-1443,1475-1479,
+ * 1526-1530); the definition is the builder's, stated in include/voxcore_gpu.h (vc_cell_circum_angle_grid): per cell of
+ * the 7 anchored at a vertex, valid iff all its vertices are inside (else 0), P = distinct closest sites of its vertices,
+ * m = its centre; circumradius = radius of the smallest ball enclosing P, angle = max over pairs of angle(p-m, q-m)/2.
+ * The smallest enclosing ball is written here the textbook way (Welzl's recursion on the boundary set), not as the
+ * kernel's enumeration, so the two only share the definition.  id / inside: planes [z0, min(z1+1, nz)); out [7][z1-z0][y][x]. */
+typedef struct
+{
+    double c[3], r2;
+    int ok;
+} orc_ball;
+static orc_ball orc_ball_of(const double (*b)[3], int nb)
+{
+    orc_ball B = {{0, 0, 0}, -1.0, 1};
+    if (nb == 0)
+        return B;
+    if (nb == 1)
+    {
+        memcpy(B.c, b[0], sizeof B.c);
+        B.r2 = 0;
+        return B;
+    }
+    /* centre = b0 + sum_k l_k (b_k - b0) with  2 (b_j - b0).(centre - b0) = |b_j - b0|^2 : Gram system, Gaussian elimination */
+    double A[3][4];
+    int m = nb - 1;
+    for (int j = 0; j < m; ++j)
+    {
+        for (int k = 0; k < m; ++k)
+        {
+            double d = 0;
+            for (int t = 0; t < 3; ++t)
+                d += (b[j + 1][t] - b[0][t]) * (b[k + 1][t] - b[0][t]);
+            A[j][k] = 2 * d;
+        }
+        double d = 0;
+        for (int t = 0; t < 3; ++t)
+            d += (b[j + 1][t] - b[0][t]) * (b[j + 1][t] - b[0][t]);
+        A[j][m] = d;
+    }
+    for (int col = 0; col < m; ++col)
+    {
+        int piv = col;
+        for (int r = col + 1; r < m; ++r)
+            if (fabs(A[r][col]) > fabs(A[piv][col]))
+                piv = r;
+        if (fabs(A[piv][col]) < 1e-12)
+        {
+            B.ok = 0; /* affinely dependent boundary set */
+            return B;
+        }
+        for (int k = 0; k <= m; ++k)
+        {
+            double t = A[col][k];
+            A[col][k] = A[piv][k];
+            A[piv][k] = t;
+        }
+        for (int r = 0; r < m; ++r)
+            if (r != col)
+            {
+                double f = A[r][col] / A[col][col];
+                for (int k = col; k <= m; ++k)
+                    A[r][k] -= f * A[col][k];
+            }
+    }
+    double off[3] = {0, 0, 0};
+    for (int j = 0; j < m; ++j)
+        for (int t = 0; t < 3; ++t)
+            off[t] += A[j][m] / A[j][j] * (b[j + 1][t] - b[0][t]);
+    B.r2 = off[0] * off[0] + off[1] * off[1] + off[2] * off[2];
+    for (int t = 0; t < 3; ++t)
+        B.c[t] = b[0][t] + off[t];
+    return B;
+}
+static orc_ball orc_welzl(const double (*p)[3], int n, double (*b)[3], int nb)
+{
+    if (n == 0 || nb == 4)
+        return orc_ball_of((const double (*)[3])b, nb);
+    orc_ball B = orc_welzl(p, n - 1, b, nb);
+    const double* q = p[n - 1];
+    double d2 = 0;
+    for (int t = 0; t < 3; ++t)
+        d2 += (q[t] - B.c[t]) * (q[t] - B.c[t]);
+    if (B.ok && B.r2 >= 0 && d2 <= B.r2 * (1.0 + 1e-12) + 1e-12)
+        return B;
+    memcpy(b[nb], q, 3 * sizeof(double));
+    return orc_welzl(p, n - 1, b, nb + 1);
+}
+void orc_cell_circum_angle_grid(const float* sites_xyz, const int32_t* id, const uint8_t* inside, int nx, int ny, int nz, int z0,
+                                int z1, double* circ7, double* ang7)
+{
+    static const int CELLS[7][8] = {{0, 1, -1}, {0, 2, -1}, {0, 4, -1}, {0, 1, 2, 3, -1}, {0, 1, 4, 5, -1}, {0, 2, 4, 6, -1},
+                                    {0, 1, 2, 3, 4, 5, 6, 7}};
+    static const int NV[7] = {2, 2, 2, 4, 4, 4, 8};
+    const int zh = z1 < nz ? z1 + 1 : z1;
+    const size_t plane = (size_t)nx * ny, nv = plane * (size_t)(z1 - z0);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+            {
+                const size_t o = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)(z - z0));
+                for (int cell = 0; cell < 7; ++cell)
+                {
+                    double P[8][3], m[3] = {0, 0, 0};
+                    int ids[8], n = 0, valid = 1;
+                    for (int k = 0; k < NV[cell]; ++k)
+                    {
+                        const int c = CELLS[cell][k];
+                        const int xx = x + (c & 1), yy = y + ((c >> 1) & 1), zz = z + (c >> 2);
+                        m[0] += xx, m[1] += yy, m[2] += zz;
+                        if (!(xx < nx && yy < ny && zz < zh))
+                        {
+                            valid = 0;
+                            continue;
+                        }
+                        const size_t q = (size_t)xx + (size_t)nx * ((size_t)yy + (size_t)ny * (size_t)(zz - z0));
+                        if (!inside[q])
+                        {
+                            valid = 0;
+                            continue;
+                        }
+                        int seen = 0;
+                        for (int j = 0; j < n; ++j)
+                            seen |= ids[j] == id[q];
+                        if (!seen)
+                        {
+                            ids[n] = id[q];
+                            for (int t = 0; t < 3; ++t)
+                                P[n][t] = (double)sites_xyz[3 * (size_t)id[q] + t];
+                            ++n;
+                        }
+                    }
+                    double r = 0, a = 0;
+                    if (valid && n > 1)
+                    {
+                        double b[4][3];
+                        orc_ball B = orc_welzl((const double (*)[3])P, n, b, 0);
+                        r = sqrt(B.r2 > 0 ? B.r2 : 0);
+                        for (int t = 0; t < 3; ++t)
+                            m[t] /= NV[cell];
+                        for (int i = 0; i < n; ++i)
+                            for (int j = i + 1; j < n; ++j)
+                            {
+                                double uu = 0, vv = 0, uv = 0;
+                                for (int t = 0; t < 3; ++t)
+                                {
+                                    const double u = P[i][t] - m[t], v = P[j][t] - m[t];
+                                    uu += u * u, vv += v * v, uv += u * v;
+                                }
+                                if (uu <= 0 || vv <= 0)
+                                    continue;
+                                double cs = uv / sqrt(uu * vv);
+                                cs = cs > 1 ? 1 : (cs < -1 ? -1 : cs);
+                                const double h = 0.5 * acos(cs);
+                                a = h > a ? h : a;
+                            }
+                    }
+                    circ7[(size_t)cell * nv + o] = r;
+                    ang7[(size_t)cell * nv + o] = a;
+                }
+            }
 }
 
 /* ---- next row 8(f-4): dual quads of the crossing grid edges (the medial complex of the dense product) ----------

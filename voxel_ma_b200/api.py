@@ -26,7 +26,7 @@ SYMBOLS = [
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",
     "vc_peer_buffer", "vc_peer_close", "vc_peer_set_timeout", "vc_sites_post_peers", "vc_sites_collect_peers", "vc_closest_grid",
     "vc_closest_points", "vc_closest_points_f32", "vc_radius_search", "vc_cell_measures_grid", "vc_face_lambda", "vc_vertex_radii", "vc_segment_max", "vc_ref_counts", "vc_simple_pairs",
-    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_download_planes", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records", "vc_medial_quads_count", "vc_medial_quads",
+    "vc_run_dense", "vc_closest_and_measures", "vc_set_pipeline", "vc_download", "vc_download_planes", "vc_device_ptr", "vc_run_dense_host", "vc_compact_count", "vc_compact_records", "vc_medial_quads_count", "vc_medial_quads", "vc_cell_circum_angle_grid",
     "vc_run_dense_host_compact", "vc_run_dense_host_compact_i8", "vc_set_compact_mode", "vc_profile_enable", "vc_profile_reset",
     "vc_profile_count", "vc_profile_get", "vc_launch_count",
 ]
@@ -110,6 +110,7 @@ def load_library(path: str | None = None):
     lib.vc_device_ptr.argtypes = [vp, i32]
     lib.vc_device_ptr.restype = vp
     lib.vc_run_dense_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.vc_cell_circum_angle_grid.argtypes = [vp, i32, i32, vp, vp]
     lib.vc_medial_quads_count.argtypes = [vp, C.POINTER(i64)]
     lib.vc_medial_quads.argtypes = [vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]
     lib.vc_profile_enable.argtypes = [vp, i32]
@@ -495,6 +496,15 @@ class Context:
                                                     _ptr(d2x4), _ptr(lambda7), _ptr(radius), _ptr(id_dense), _ptr(d2x4_dense),
                                                     C.byref(ns)))
         return n.value, ns.value
+
+    def cell_circum_angle_grid(self, za=None, zb=None):
+        """(circumradius f64 [7][z][y][x], object angle f64 [7][z][y][x]) of the planes [za, zb) (default: all owned planes)"""
+        za = self.z0 if za is None else za
+        zb = self.z1 if zb is None else zb
+        circ = np.empty((7, zb - za, self.ny, self.nx), np.float64)
+        ang = np.empty_like(circ)
+        self._ck(self.lib.vc_cell_circum_angle_grid(self.h, za, zb, _ptr(circ), _ptr(ang)))
+        return circ, ang
 
     # ---- the medial complex of the dense product (csrc/vc_medial.cu)
     def medial_quads(self):

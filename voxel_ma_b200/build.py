@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvoxcore_gpu.so")
-SOURCES = ["vc_api.cu", "vc_sites.cu", "vc_edt.cu", "vc_measures.cu", "vc_points.cu", "vc_mesh.cu", "vc_thin.cu", "vc_peer.cu", "vc_compact.cu", "vc_medial.cu"]
+SOURCES = ["vc_api.cu", "vc_sites.cu", "vc_edt.cu", "vc_measures.cu", "vc_points.cu", "vc_mesh.cu", "vc_thin.cu", "vc_peer.cu", "vc_compact.cu", "vc_medial.cu", "vc_circum.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
