@@ -354,6 +354,55 @@ def load_traffic(workload, kernel):
     return None, None, None
 
 
+def points_path(ctx, grid, args, nq=4_000_000):
+    """The arbitrary-point query path (vc_closest_points).  Two query sets over this workload's sites: (1) the shape the
+    reference's own callers have -- points INSIDE the solid (Voronoi vertices kept by tagVert, medial-axis vertices,
+    src/voxelapps.cpp:184-228, src/exporters.cpp:629-636): random inside grid vertices jittered by +-0.5 voxel; (2) the
+    worst case for an expanding-shell search: uniformly random points of the whole box (most of them far from any site)."""
+    nx, ny, nz = grid
+    rng = np.random.default_rng(11)
+    vert = ctx.compact_records()[0].astype(np.int64)
+    pick = vert[rng.integers(0, len(vert), nq)]
+    q_in = np.stack([pick % nx, (pick // nx) % ny, pick // (nx * ny)], -1).astype(np.float64) + rng.uniform(-0.5, 0.5, (nq, 3))
+    q_box = np.stack([rng.uniform(-0.5, nx - 0.5, nq), rng.uniform(-0.5, ny - 0.5, nq), rng.uniform(-0.5, nz - 0.5, nq)], -1)
+    del vert, pick
+    ctx.closest_points(q_in[:4096])  # builds the cell list of the resident sites (lazily, once per site set)
+    out = {"sites": ctx.num_sites(), "note": "vc_closest_points from host arrays (copies inside the timed call): queries sorted by "
+           "cell on the device, exact expanding-shell search over the cell list, double precision, ties to the lowest id"}
+    for name, q in (("inside_queries", q_in), ("box_queries", q_box)):
+        ctx.closest_points(q)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ids, d2 = ctx.closest_points(q)
+            ts.append(time.perf_counter() - t0)
+        ctx.profile(True)
+        ctx.profile_reset()
+        ctx.closest_points(q)
+        prof = {k: round(v["ms"], 4) for k, v in ctx.profile_report().items()}
+        ctx.profile(False)
+        rec = {"queries": nq, "gpu_q_per_s": nq / float(np.median(ts)), "gpu_ms_per_call": float(np.median(ts)) * 1e3,
+               "gpu_kernels_ms": prof, "h2d_bytes": int(q.nbytes), "d2h_bytes": int(ids.nbytes + d2.nbytes),
+               "mean_distance": float(np.sqrt(d2).mean())}
+        if not args.no_cpu_baseline:
+            import multiprocessing as mp
+            from oracle import bindings as ob
+            if ob.have_ref():
+                cores = os.cpu_count() or 1
+                sites = ctx.get_sites().astype(np.float64)
+                m = 20000
+                with quiet_stdout():
+                    with mp.get_context("fork").Pool(cores) as pool:
+                        secs = pool.map(_ann_worker, [(sites, q[k * m:(k + 1) * m]) for k in range(cores)])
+                    a_id, a_d2 = ob.ref_ann(sites, q[:m])
+                rec["cpu_ann"] = {"q_per_s": cores * m / max(secs), "cores": cores, "queries": cores * m, "kind": "reference",
+                                  "note": "ANNkd_tree build + annkSearch(k=1, eps=0), one forked process per core"}
+                # same answers: distance exactly, id up to ANN's traversal-dependent choice among equidistant sites
+                rec["agrees_with_ann"] = bool(np.array_equal(a_d2, d2[:m]) and ((ids[:m] == a_id) | (ids[:m] < a_id)).all())
+        out[name] = rec
+    return out
+
+
 def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
     """One workload on this process group.  Returns the JSON line (rank 0) or None.  sub=True: the condensed record of
     the secondary N=1 workload ("at_512"): value, e2e and rooflines only."""
@@ -681,6 +730,14 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
                                              "each step) + sites + closest + measures; wall clock per step"}
             except Exception as ex:
                 line["mesh_path"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_points:
+        # the arbitrary-point query path (vc_closest_points: the drop-in for ANNkd_tree::annkSearch(k=1, eps=0) behind
+        # voxelapps / estimateRadiiField): uniformly random float64 queries in the grid's box over this workload's sites,
+        # host arrays in and out; next to it the reference's kd-tree on all host cores over a sample of the same queries
+        try:
+            line["points_path"] = points_path(ctx, grid, args)
+        except Exception as ex:
+            line["points_path"] = {"error": repr(ex)}
     barrier()
     if state.get("peers") is not None:
         state["peers"].close()
@@ -749,6 +806,7 @@ def main():
     ap.add_argument("--weak", action="store_true", help="weak scaling instead: 512^3 vertices per GPU (twist512 at N=1, assembly family "
                     "512x512x1024 / 512x1024x1024 / 1024^3 at N=2/4/8)")
     ap.add_argument("--no-at512", action="store_true", help="N=1: skip the secondary twist512 measurement")
+    ap.add_argument("--no-points", action="store_true", help="N=1: skip the arbitrary-point query leg (points_path)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--balance", type=float, default=0.0, help="N>1: weight c of the per-plane inside fraction in the slab-height "
                     "estimate 1 + c*fraction (0 = equal weights)")

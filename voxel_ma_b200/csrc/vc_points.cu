@@ -9,6 +9,14 @@
 // accumulated x,y,z (3rdparty/ann/src/ANN.cpp:43-58), no FMA contraction; ties go to the lowest
 // site id (3rdparty/ann/src/brute.cpp:56-82 -- the kd-tree returns the same distance but an
 // order-dependent id).
+//
+// Memory behaviour (round 2): a cell's sites are packed next to each other as 32-byte records (x, y, z doubles +
+// id), read with two 128-bit loads through the read-only path; the cell offsets come from the boundaries of the
+// sorted keys (no search per cell); and vc_closest_points SORTS THE QUERIES by cell first (the same device radix
+// sort), so the lanes of a warp search the same or neighbouring cells at the same time -- their loads of a site are
+// one broadcast out of L1 instead of 32 scattered sector reads.  Staging a cell neighbourhood in shared memory per
+// block was weighed and dropped: the reference's query sets (Voronoi vertices, medial-axis vertices, skeleton points:
+// about one query per occupied cell) leave nothing to share beyond what the sort already makes L1 do.
 #include <cmath>
 #include <vector>
 
@@ -20,6 +28,25 @@ struct CellGrid
     double h, inv_h;
     int dim[3];
 };
+
+// a site as the searches read it: 32 bytes, aligned, two 128-bit loads
+struct __align__(32) CSite
+{
+    double x, y, z;
+    int id, pad;
+};
+__device__ __forceinline__ CSite cs_load(const CSite* __restrict__ p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    CSite s;
+    s.x = a.x;
+    s.y = a.y;
+    s.z = b.x;
+    s.id = __double_as_longlong(b.y) & 0xFFFFFFFFll;
+    s.pad = 0;
+    return s;
+}
 
 __device__ __forceinline__ int cg_cell(const CellGrid& g, double v, int a)
 {
@@ -37,49 +64,48 @@ __global__ void k_cell_keys(const double* __restrict__ s, int64_t n, CellGrid g,
     val[i] = (u32)i;
 }
 
+// ptr[c] = first sorted position whose cell is >= c, from the boundaries of the sorted keys: position i fills the
+// cells (key[i-1], key[i]] (position n fills the tail), so every cell is written exactly once and nothing is searched
 __global__ void k_cell_ptr(const u64* __restrict__ key_sorted, int64_t n, int64_t ncells, int* __restrict__ ptr)
 {
-    int64_t cidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cidx > ncells)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n)
         return;
-    int64_t lo = 0, hi = n;
-    while (lo < hi)
-    {
-        int64_t mid = (lo + hi) >> 1;
-        if (key_sorted[mid] < (u64)cidx)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    ptr[cidx] = (int)lo;
+    const int64_t lo = i == 0 ? 0 : (int64_t)key_sorted[i - 1] + 1;
+    const int64_t hi = i == n ? ncells : (int64_t)key_sorted[i];
+    for (int64_t c = lo; c <= hi; ++c)
+        ptr[c] = (int)i;
 }
 
-// sites of a cell, in ascending id order, re-packed next to each other: (x,y,z) doubles + id
-__global__ void k_cell_gather(const double* __restrict__ s, const u32* __restrict__ ids, int64_t n, double* __restrict__ packed,
-                              int* __restrict__ ent)
+// sites of a cell, in ascending id order, re-packed next to each other as 32-byte records
+__global__ void k_cell_gather(const double* __restrict__ s, const u32* __restrict__ ids, int64_t n, CSite* __restrict__ packed)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
     u32 id = ids[i];
-    packed[3 * i] = s[3 * (size_t)id];
-    packed[3 * i + 1] = s[3 * (size_t)id + 1];
-    packed[3 * i + 2] = s[3 * (size_t)id + 2];
-    ent[i] = (int)id;
+    CSite r;
+    r.x = s[3 * (size_t)id];
+    r.y = s[3 * (size_t)id + 1];
+    r.z = s[3 * (size_t)id + 2];
+    r.id = (int)id;
+    r.pad = 0;
+    packed[i] = r;
 }
 
-__device__ __forceinline__ void scan_cell(const double* __restrict__ ps, const int* __restrict__ ent, int b, int e, double q0,
-                                          double q1, double q2, double& best, int& bid)
+__device__ __forceinline__ void scan_cell(const CSite* __restrict__ ps, int b, int e, double q0, double q1, double q2, double& best,
+                                          int& bid)
 {
     for (int k = b; k < e; ++k)
     {
-        double t = __dsub_rn(q0, ps[3 * k]);
+        const CSite p = cs_load(ps + k);
+        double t = __dsub_rn(q0, p.x);
         double d = __dmul_rn(t, t);
-        t = __dsub_rn(q1, ps[3 * k + 1]);
+        t = __dsub_rn(q1, p.y);
         d = __dadd_rn(d, __dmul_rn(t, t));
-        t = __dsub_rn(q2, ps[3 * k + 2]);
+        t = __dsub_rn(q2, p.z);
         d = __dadd_rn(d, __dmul_rn(t, t));
-        int id = ent[k];
+        const int id = p.id;
         if (d < best || (d == best && id < bid))
         {
             best = d;
@@ -90,19 +116,20 @@ __device__ __forceinline__ void scan_cell(const double* __restrict__ ps, const i
 
 // float32 variant: trimesh::KDtree's distance (3rdparty/trimesh2/libsrc/KDtree.cc:28-33), sqr(x0-y0) + sqr(x1-y1) +
 // sqr(x2-y2) in float with x = the tree point; sites and query are floats widened exactly, so the casts are lossless
-__device__ __forceinline__ void scan_cell_f32(const double* __restrict__ ps, const int* __restrict__ ent, int b, int e, double q0,
-                                              double q1, double q2, double& best, int& bid)
+__device__ __forceinline__ void scan_cell_f32(const CSite* __restrict__ ps, int b, int e, double q0, double q1, double q2,
+                                              double& best, int& bid)
 {
     const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2;
     for (int k = b; k < e; ++k)
     {
-        float t = __fsub_rn((float)ps[3 * k], f0);
+        const CSite p = cs_load(ps + k);
+        float t = __fsub_rn((float)p.x, f0);
         float d = __fmul_rn(t, t);
-        t = __fsub_rn((float)ps[3 * k + 1], f1);
+        t = __fsub_rn((float)p.y, f1);
         d = __fadd_rn(d, __fmul_rn(t, t));
-        t = __fsub_rn((float)ps[3 * k + 2], f2);
+        t = __fsub_rn((float)p.z, f2);
         d = __fadd_rn(d, __fmul_rn(t, t));
-        int id = ent[k];
+        const int id = p.id;
         if ((double)d < best || ((double)d == best && id < bid))
         {
             best = (double)d;
@@ -116,12 +143,14 @@ __device__ __forceinline__ void scan_cell_f32(const double* __restrict__ ps, con
 template <bool GRID, bool F32 = false>
 __global__ void __launch_bounds__(128)
     k_closest_points(const double* __restrict__ q, int64_t n, CellGrid g, const int* __restrict__ ptr,
-                     const double* __restrict__ ps, const int* __restrict__ ent, int nx, int ny, int z0, int* __restrict__ id_out,
+                     const CSite* __restrict__ ps, const u32* __restrict__ order, int nx, int ny, int z0, int* __restrict__ id_out,
                      double* __restrict__ d2_out, u32* __restrict__ d2x4_out, double max_d2 = INFINITY)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
+    if (order)
+        i = (int64_t)order[i]; // queries are taken in cell order: neighbouring lanes search the same cells
     double q0, q1, q2;
     if (GRID)
     {
@@ -145,9 +174,9 @@ __global__ void __launch_bounds__(128)
     auto scan = [&](int b, int e)
     {
         if (F32)
-            scan_cell_f32(ps, ent, b, e, q0, q1, q2, best, bid);
+            scan_cell_f32(ps, b, e, q0, q1, q2, best, bid);
         else
-            scan_cell(ps, ent, b, e, q0, q1, q2, best, bid);
+            scan_cell(ps, b, e, q0, q1, q2, best, bid);
     };
     for (int r = 0; r <= rmax; ++r)
     {
@@ -186,6 +215,17 @@ __global__ void __launch_bounds__(128)
         d2_out[i] = best;
     if (d2x4_out)
         d2x4_out[i] = bid < 0 ? 0xFFFFFFFFu : (u32)__double2ll_rn(4.0 * best);
+}
+
+// cell key of every query (for the sort that puts neighbouring queries into neighbouring lanes)
+__global__ void k_query_keys(const double* __restrict__ q, int64_t n, CellGrid g, u64* __restrict__ key, u32* __restrict__ val)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int cx = cg_cell(g, q[3 * i], 0), cy = cg_cell(g, q[3 * i + 1], 1), cz = cg_cell(g, q[3 * i + 2], 2);
+    key[i] = ((u64)cz * g.dim[1] + cy) * g.dim[0] + cx;
+    val[i] = (u32)i;
 }
 
 static CellGrid g_of(const vc_ctx* c)
@@ -233,9 +273,8 @@ static int build_from_device_sites(vc_ctx* c, const double* dsites, int64_t n, c
     VC_CUDA(c, c->sv0.ensure((size_t)(n + 1) * 4));
     VC_CUDA(c, c->sv1.ensure((size_t)(n + 1) * 4));
     VC_CUDA(c, c->cl_ptr.ensure((size_t)(ncells + 2) * 4));
-    VC_CUDA(c, c->cl_ent.ensure((size_t)(n + 1) * 4));
     DevBuf packed;
-    VC_CUDA(c, packed.ensure((size_t)(n + 1) * 24));
+    VC_CUDA(c, packed.ensure((size_t)(n + 1) * sizeof(CSite)));
     u64* k = c->sk0.as<u64>();
     u32* v = c->sv0.as<u32>();
     unsigned blocks = vc_blocks((size_t)(n > 0 ? n : 1), 256);
@@ -247,9 +286,9 @@ static int build_from_device_sites(vc_ctx* c, const double* dsites, int64_t n, c
     int s = vc_radix_sort_pairs(c, n, bits, &k, &v);
     if (s == VC_OK)
     {
-        VC_LAUNCH(c, "cell_ptr", k_cell_ptr, vc_blocks((size_t)ncells + 1, 256), 256, 0, k, n, ncells, c->cl_ptr.as<int>());
+        VC_LAUNCH(c, "cell_ptr", k_cell_ptr, vc_blocks((size_t)n + 1, 256), 256, 0, k, n, ncells, c->cl_ptr.as<int>());
         if (n)
-            VC_LAUNCH(c, "cell_gather", k_cell_gather, blocks, 256, 0, dsites, v, n, packed.as<double>(), c->cl_ent.as<int>());
+            VC_LAUNCH(c, "cell_gather", k_cell_gather, blocks, 256, 0, dsites, v, n, packed.as<CSite>());
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess)
             s = vc_fail(c, VC_ERR_CUDA, "cell list", e);
@@ -348,10 +387,30 @@ int st_closest_points(vc_ctx* c, const double* q, int64_t n, int32_t* id, double
         e = dd.ensure((size_t)n * 8);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(dq.p, q, (size_t)n * 24, cudaMemcpyDefault, c->stream);
+    const u32* order = nullptr;
+    if (e == cudaSuccess && n >= 4096 && n < ((int64_t)1 << 31))
+    { // the queries in cell order (the cell list's own buffers are free again: it keeps only cl_ptr and the packed sites)
+        e = c->sk0.ensure((size_t)(n + 1) * 8);
+        e = e == cudaSuccess ? c->sk1.ensure((size_t)(n + 1) * 8) : e;
+        e = e == cudaSuccess ? c->sv0.ensure((size_t)(n + 1) * 4) : e;
+        e = e == cudaSuccess ? c->sv1.ensure((size_t)(n + 1) * 4) : e;
+        if (e == cudaSuccess)
+        {
+            u64* k = c->sk0.as<u64>();
+            u32* v = c->sv0.as<u32>();
+            const CellGrid g = g_of(c);
+            VC_LAUNCH(c, "query_keys", k_query_keys, vc_blocks((size_t)n, 256), 256, 0, dq.as<double>(), n, g, k, v);
+            int bits = 1;
+            while (bits < 62 && (((u64)g.dim[0] * g.dim[1] * g.dim[2]) >> bits))
+                ++bits;
+            if (vc_radix_sort_pairs(c, n, bits, &k, &v) == VC_OK)
+                order = v;
+        }
+    }
     if (e == cudaSuccess)
     {
         VC_LAUNCH(c, "closest_points", (k_closest_points<false>), vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), n,
-                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), 0, 0, 0, did.as<int>(),
+                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<CSite>(), order, 0, 0, 0, did.as<int>(),
                   dd.as<double>(), (u32*)nullptr);
         e = cudaMemcpyAsync(id, did.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
         if (e == cudaSuccess && d2)
@@ -392,7 +451,7 @@ int st_closest_points_f32(vc_ctx* c, const float* q, int64_t n, float max_d2, in
     {
         const double lim = (max_d2 > 0.0f && max_d2 < INFINITY) ? (double)max_d2 : (double)INFINITY;
         VC_LAUNCH(c, "closest_points_f32", (k_closest_points<false, true>), vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), n,
-                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), 0, 0, 0, did.as<int>(),
+                  g_of(c), c->cl_ptr.as<int>(), c->gsites.as<CSite>(), (const u32*)nullptr, 0, 0, 0, did.as<int>(),
                   ddv.as<double>(), (u32*)nullptr, lim);
         e = cudaMemcpyAsync(id, did.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
         if (e == cudaSuccess)
@@ -423,7 +482,7 @@ int st_closest_points_f32(vc_ctx* c, const float* q, int64_t n, float max_d2, in
 // =============================================================================================
 __global__ void __launch_bounds__(128)
     k_radius_search(const double* __restrict__ q, const double* __restrict__ sq_rad, int64_t n, CellGrid g, const int* __restrict__ ptr,
-                    const double* __restrict__ ps, const int* __restrict__ ent, const int64_t* __restrict__ off, int* __restrict__ count,
+                    const CSite* __restrict__ ps, const int64_t* __restrict__ off, int* __restrict__ count,
                     int* __restrict__ idx, double* __restrict__ dd)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,18 +515,19 @@ __global__ void __launch_bounds__(128)
                 const int b = ptr[rowc + xl], e = ptr[rowc + xh + 1]; // the x-run is contiguous in the list
                 for (int k = b; k < e; ++k)
                 {
-                    double t = __dsub_rn(q0, ps[3 * k]);
+                    const CSite p = cs_load(ps + k);
+                    double t = __dsub_rn(q0, p.x);
                     double d = __dmul_rn(t, t);
-                    t = __dsub_rn(q1, ps[3 * k + 1]);
+                    t = __dsub_rn(q1, p.y);
                     d = __dadd_rn(d, __dmul_rn(t, t));
-                    t = __dsub_rn(q2, ps[3 * k + 2]);
+                    t = __dsub_rn(q2, p.z);
                     d = __dadd_rn(d, __dmul_rn(t, t));
                     if (!(d <= R2))
                         continue;
                     ++cnt;
                     if (!cap)
                         continue;
-                    const int id = ent[k];
+                    const int id = p.id;
                     // insertion into the sorted row (distance, id); the last one falls off when full
                     int pos = have;
                     if (have == cap)
@@ -533,7 +593,7 @@ int st_radius_search(vc_ctx* c, const double* q, const double* sq_rad, int64_t n
     if (e == cudaSuccess)
     {
         VC_LAUNCH(c, "radius_search", k_radius_search, vc_blocks((size_t)n, 128), 128, 0, dq.as<double>(), dr.as<double>(), n, g_of(c),
-                  c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), off ? doff.as<int64_t>() : (const int64_t*)nullptr,
+                  c->cl_ptr.as<int>(), c->gsites.as<CSite>(), off ? doff.as<int64_t>() : (const int64_t*)nullptr,
                   dcnt.as<int>(), didx.as<int>(), ddd.as<double>());
         if (count)
             e = cudaMemcpyAsync(count, dcnt.p, (size_t)n * 4, cudaMemcpyDefault, c->stream);
@@ -559,7 +619,7 @@ int st_closest_general_grid(vc_ctx* c)
     VC_CUDA(c, c->id.ensure(nv * 4));
     VC_CUDA(c, c->d2.ensure(nv * 4));
     VC_LAUNCH(c, "closest_grid_celllist", (k_closest_points<true>), vc_blocks(nv, 128), 128, 0, (const double*)nullptr,
-              (int64_t)nv, g_of(c), c->cl_ptr.as<int>(), c->gsites.as<double>(), c->cl_ent.as<int>(), c->nx, c->ny, c->z0,
+              (int64_t)nv, g_of(c), c->cl_ptr.as<int>(), c->gsites.as<CSite>(), (const u32*)nullptr, c->nx, c->ny, c->z0,
               c->id.as<int>(), (double*)nullptr, c->d2.as<u32>());
     VC_CUDA(c, cudaGetLastError());
     c->have_closest = true;
