@@ -42,6 +42,10 @@ typedef enum vc_status
     VC_ERR_UNSUPPORTED = -5  /* valid request this build does not implement */
 } vc_status;
 
+/* Starts the CUDA driver and the device's primary context, nothing else (no vc_ctx, no message): a host program may call
+ * it from a helper thread at start-up so that the seconds this takes on a cold GPU pass while it reads its input
+ * (voxel_ma_b200/host/dropin/gpu_surfacing.cpp does, for the reference CLI).  VC_OK or VC_ERR_CUDA. */
+int vc_warmup(int device);
 /* ---- context ------------------------------------------------------------------------------ */
 int vc_abi_version(void);
 int vc_ctx_create(int device, vc_ctx** out);

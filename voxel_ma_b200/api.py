@@ -20,7 +20,7 @@ ARR_INSIDE, ARR_ID, ARR_D2X4, ARR_EDGE3, ARR_FACE3, ARR_CUBE, ARR_RADIUS = range
 
 # every symbol include/voxcore_gpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "vc_abi_version", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
+    "vc_abi_version", "vc_warmup", "vc_ctx_create", "vc_ctx_destroy", "vc_last_error", "vc_stream", "vc_synchronize",
     "vc_host_alloc", "vc_host_free", "vc_set_grid", "vc_volume_upload_f32", "vc_volume_upload_i8", "vc_volume_upload_f64_zfast",
     "vc_classify_grid", "vc_classify_points", "vc_classify_mesh", "vc_extract_sites", "vc_get_sites", "vc_set_sites", "vc_num_sites",
     "vc_sites_detect_local", "vc_sites_export_local", "vc_sites_import_global", "vc_peer_create", "vc_peer_open", "vc_peer_open_ptrs",

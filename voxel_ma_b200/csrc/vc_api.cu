@@ -87,6 +87,18 @@ extern "C"
 {
     int vc_abi_version(void) { return VC_ABI_VERSION; }
 
+    int vc_warmup(int device)
+    { // driver + primary-context start-up only (seconds on a box without a persistence daemon): safe from any thread
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess ||
+            cudaFree(nullptr) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return VC_ERR_CUDA;
+        }
+        return VC_OK;
+    }
+
     int vc_ctx_create(int device, vc_ctx** out)
     {
         if (!out)

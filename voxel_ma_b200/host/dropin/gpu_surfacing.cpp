@@ -19,6 +19,32 @@
 SurfacerErrCode ref_extractBoundaryVts(Surfacer* self, const std::shared_ptr<Volume3DScalar>& vol, std::vector<point>& vts) asm(
     "vcref_Surfacer_extractBoundaryVts");
 
+#include <thread>
+
+namespace
+{
+// The CLI reads its volume first (src/voroUtility.cpp:454-470; one fread per voxel, seconds at 256^3) and only then reaches
+// the first GPU call.  Starting the CUDA driver / primary context takes seconds on a cold GPU, so it is started here, at
+// load time, on a helper thread: by the time computeVD asks for the session the device is up.  Silent: a mode that never
+// touches the GPU (or a box without one) sees no message from this; the session reports a missing device when it is used.
+struct WarmUp
+{
+    std::thread t;
+    WarmUp()
+    {
+        t = std::thread([] {
+            const char* dev = std::getenv("VC_DEVICE");
+            vc_warmup(dev ? std::atoi(dev) : 0);
+        });
+    }
+    ~WarmUp()
+    {
+        if (t.joinable())
+            t.join();
+    }
+} g_warm_up;
+} // namespace
+
 namespace vcgpu
 {
 // Pulls a dense volume through the reference's accessor into Tao's in-memory order and makes it
@@ -29,6 +55,7 @@ bool make_resident(const std::shared_ptr<Volume3DScalar>& vol)
     if (!s.ok())
         return false;
     const int nx = vol->getSizeX(), ny = vol->getSizeY(), nz = vol->getSizeZ();
+    TraceScope tr("make_resident (volume pull + upload + classify)");
     std::vector<double> zfast((size_t)nx * ny * nz);
     const Volume3DScalar* v = vol.get(); // the const accessor: a plain array read, safe from several threads
 #pragma omp parallel for schedule(static)
@@ -55,6 +82,7 @@ SurfacerErrCode Surfacer::extractBoundaryVts(const shared_ptr<Volume3DScalar>& _
         std::cout << "Error: no GPU context; exiting." << std::endl;
         std::exit(1);
     }
+    vcgpu::TraceScope tr("Surfacer::extractBoundaryVts (GPU)");
     if (!vcgpu::make_resident(_vol))
         return SurfacerErrCode::FAILURE;
     std::vector<float> xyz;

@@ -46,6 +46,7 @@ static void all_face_lambdas(const std::vector<point>& sites, const std::vector<
 {
     Session& s = Session::get();
     static_assert(sizeof(point) == 12 && sizeof(ivec2) == 8, "trimesh::Vec is a plain array");
+    TraceScope tr("all_face_lambdas (set_sites + vc_face_lambda)");
     if (!s.set_sites(sites.empty() ? nullptr : &sites[0][0], (int64_t)sites.size()))
         die("vc_set_sites");
     lam.assign(face_sites.size(), 0.0f);
@@ -183,6 +184,7 @@ void VoroInfo::computeFacesMeasure(MeasureForMA::meassuretype _mssure_tp, const 
     _faces_msure.clear();
     if (_mssure_tp != MeasureForMA::LAMBDA)
         return;
+    vcgpu::TraceScope tr("computeFacesMeasure");
     std::vector<ivec2> pairs;
     pairs.reserve(_faces_indices.size());
     for (int fi : _faces_indices)
@@ -194,6 +196,7 @@ void VoroInfo::computeFacesMeasure(MeasureForMA::meassuretype _mssure_tp, const 
 static void max_lambda_over_faces(const VoroInfo& voro, const std::vector<point>& sites, const std::vector<ivec2>& face_sites,
                                   const std::vector<int32_t>& off, const std::vector<int32_t>& items, vector<float>& out)
 {
+    vcgpu::TraceScope tr("max_lambda_over_faces (lambdas + validity + vc_segment_max)");
     std::vector<float> lam;
     vcgpu::all_face_lambdas(sites, face_sites, lam);
     std::vector<uint8_t> valid(face_sites.size());
@@ -216,6 +219,7 @@ void VoroInfo::computeEdgesMeasure(MeasureForMA::meassuretype _mssure_tp, const 
     _edges_msure.clear();
     if (_mssure_tp != MeasureForMA::LAMBDA)
         return;
+    vcgpu::TraceScope tr("computeEdgesMeasure");
     std::vector<int32_t> off(1, 0), items;
     for (int ei : _edges_indices)
     {
@@ -233,6 +237,7 @@ void VoroInfo::computeVertexMeasure(MeasureForMA::meassuretype _mssure_tp, const
     _vts_msure.clear();
     if (_mssure_tp != MeasureForMA::LAMBDA)
         return;
+    vcgpu::TraceScope tr("computeVertexMeasure");
     std::vector<int32_t> off(1, 0), items;
     for (int vi : _vts_indices)
     {

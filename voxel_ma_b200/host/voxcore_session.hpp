@@ -18,8 +18,30 @@
 
 #include "voxcore_gpu.h"
 
+#include <chrono>
+
 namespace vcgpu
 {
+// VC_DROPIN_TRACE=1: wall time of the drop-in's steps on stderr (where does a drop-in call spend its time: host marshalling,
+// the ABI call, the copies) -- the reference's own `time -> ...` lines stay what they are
+struct TraceScope
+{
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit TraceScope(const char* w) : what(w), t0(std::chrono::steady_clock::now())
+    {
+        static const bool enabled = std::getenv("VC_DROPIN_TRACE") != nullptr;
+        on = enabled;
+    }
+    ~TraceScope()
+    {
+        if (on)
+            std::cerr << "[vc dropin] " << what << ": "
+                      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << " ms" << std::endl;
+    }
+};
+
 // 64-bit FNV-1a over a byte range: identity of a resident sample set / volume payload
 inline uint64_t fingerprint(const void* p, size_t n, uint64_t h = 1469598103934665603ull)
 {
