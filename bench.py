@@ -554,7 +554,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
         (h2d,) = total(pin_vol.array.nbytes)
         s3 = (z1 - z0, ny, nx)
         small = nv_local <= 160_000_000  # the variants that return dense planes need 8..41 B of pinned memory per vertex
-        if small and not sub:
+        if small:
             outs = {
                 "inside": api.PinnedArray(s3, np.uint8), "id": api.PinnedArray(s3, np.int32), "d2": api.PinnedArray(s3, np.uint32),
                 "edge3": api.PinnedArray((3,) + s3, np.float32), "face3": api.PinnedArray((3,) + s3, np.float32),
@@ -617,7 +617,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
                                        "d2h_bytes_per_step": d2h, "inside_vertices": n_in_total, "result": result}
             e2e = {"value": nv_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s * 1e3, "result": result}
-            if world == 1 and small and not sub:
+            if world == 1 and small:
                 # the same pass from an MRC mode 0 (signed byte) volume -- a format the reference's reader takes as well
                 # (isosurface_tao/reader.h:235-239); the synthetic field is quantised to 1/16, which moves the surface a
                 # little, so this is another volume, timed for what the narrower upload buys
@@ -636,7 +636,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
                 del v8, rec8
                 ctx.upload_volume(pin_vol.array, zlo=lo)
                 ctx.classify_grid(fetch=False)
-            if small and not sub:
+            if small:
                 dense = (api.PinnedArray(s3, np.int32), api.PinnedArray(s3, np.uint32))
                 dt = time_e2e(lambda: step_compact((dense[0].array, dense[1].array)))
                 e2e_variants["compact_plus_dense_ids"] = {"value": nv_total / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
