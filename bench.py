@@ -687,7 +687,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
                        "slab_heights": heights,
                        "vertices_per_gpu": nv_local,
                        "exchange": ("none (one slab)" if world == 1 else
-                                    "peer memory: detection kernel stores records into every rank over NVLink (vc_peer.cu)"
+                                    "peer memory: every rank stores its sorted run of records into every rank over NVLink, ids by ranking across the runs (vc_peer.cu)"
                                     if state.get("peers") is not None else "NCCL all-gather"), "l2": "inputs larger than L2 (no flush needed)",
                        "outputs": "inside u8, id i32, 4d2 u32, 7 lambda planes f32, radius f32 (resident in HBM)",
                        "e2e_result": e2e["result"] if e2e else None},

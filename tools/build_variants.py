@@ -11,6 +11,23 @@ VARIANTS = {
     "d4_pf24": ["-DED_PFD=24"],
     "d6_pf0": ["-DED_DEPTH=6", "-DED_PFD=0"],
     "wi_nospill": ["-DWHATIF_NOSPILL"],
+    "mr2": ["-DMR_SUB=2"],
+    "mr8": ["-DMR_SUB=8"],
+    "mr16": ["-DMR_SUB=16"],
+    "mr1": ["-DMR_SUB=1"],
+    "mr_noorder": ["-DMR_ORDER=0"],
+    "mr8o": ["-DMR_SUB=8"],
+    "mr4o_s1024": ["-DMR_STAGE_MAX=1024"],
+    "mr4o_s64": ["-DMR_STAGE_MAX=64"],
+    "mr8o_s1024": ["-DMR_SUB=8", "-DMR_STAGE_MAX=1024"],
+    "mr4_order": ["-DMR_SUB=4"],
+    "mr4_s256": ["-DMR_STAGE_MAX=256"],
+    "mr4_s128": ["-DMR_STAGE_MAX=128"],
+    "mr4_s64": ["-DMR_STAGE_MAX=64"],
+    "mr2_s256": ["-DMR_SUB=2", "-DMR_STAGE_MAX=256"],
+    "mr2_s128": ["-DMR_SUB=2", "-DMR_STAGE_MAX=128"],
+    "mr2_s64": ["-DMR_SUB=2", "-DMR_STAGE_MAX=64"],
+    "mr4_s4096": ["-DMR_STAGE_MAX=4096"],
 }
 names = sys.argv[1:] or list(VARIANTS)
 for n in names:

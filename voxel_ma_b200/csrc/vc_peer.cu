@@ -113,6 +113,15 @@ __global__ void k_peer_wait(const u64* __restrict__ my_hdr, int world, u64 seq, 
         worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
     if (p < world)
         off[p] = incl - mine;
+    // res[2 + k] = the run that is k-th shortest (k_merge_rank starts with the short ones)
+    int place = 0;
+    for (int t = 0; t < world; ++t)
+    {
+        const u64 nt = __shfl_sync(0xffffffffu, mine, t);
+        place += nt < mine || (nt == mine && t < p);
+    }
+    if (p < world)
+        res[2 + place] = (u64)p;
     if (p == world - 1)
     {
         off[world] = incl;
@@ -150,53 +159,159 @@ __device__ __forceinline__ u64 peer_lower_bound(const u64* __restrict__ k, u64 l
     return lo;
 }
 
-// id of a record = its index in its own run + the number of smaller keys in every other run.  One warp takes 32
-// consecutive records of one run: lane q brackets the block's first key in run q and lane 16 + q its last key (two
-// full binary searches per other run, done by different lanes at once), then every lane searches only inside those
-// brackets -- consecutive keys of a run are close in the other runs as well.  Writes the merged tables in id order.
+// id of a record = its index in its own run + the number of smaller keys in every other run.  One warp takes
+// 32 * MR_SUB consecutive records of one run: lane q brackets the block's first key in run q and lane 16 + q its last key
+// (two full binary searches per other run, done by different lanes at once).  The keys of run q between the two
+// brackets -- about as many as the warp's own, consecutive keys of a run are close in the other runs as well -- are then
+// staged through shared memory with coalesced loads (unless the bracket is long: where this run has a gap, another
+// run may have 1e5 keys between two of this run's), and every lane ranks its keys there: per-lane searches in global
+// memory cost a 32-byte sector per 8-byte probe, and their volume, not their latency, is what bounded this kernel
+// (0.23 ms for 2.7e6 records whichever way the searches were arranged).  Writes the merged tables in id order.
+#ifndef MR_SUB
+#define MR_SUB 4
+#endif
+#ifndef MR_ORDER
+#define MR_ORDER 1
+#endif
+#define MR_CH 256 // keys staged per round and warp
+#ifndef MR_STAGE_MAX
+#define MR_STAGE_MAX 256 // longer brackets are searched, not staged
+#endif
 __global__ void __launch_bounds__(256)
-    k_merge_rank(const u64* __restrict__ rec, int world, u64 cap, const u64* __restrict__ off, u64* __restrict__ keys_out,
-                 u64* __restrict__ corners_out)
+    k_merge_rank(const u64* __restrict__ rec, int world, u64 cap, const u64* __restrict__ off, const u64* __restrict__ order,
+                 u64* __restrict__ keys_out, u64* __restrict__ corners_out)
 {
-    const int lane = threadIdx.x & 31;
-    u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // block of 32 records, numbered run after run
-    int p = 0;
+    __shared__ u64 stage[8][MR_CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // block of 32 * MR_SUB records, numbered run after run, the SHORTEST run first: a short run is a sparse slab, whose
+    // consecutive keys have long brackets in every other run -- the slowest warps, so they start first (MR_ORDER)
+    u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int p = -1;
     u64 np = 0;
-    for (; p < world; ++p)
+#if MR_ORDER
+    for (int k = 0; k < world && p < 0; ++k)
+    {
+        const int cand = (int)order[k];
+        np = off[cand + 1] - off[cand];
+        const u64 nb = (np + 32 * MR_SUB - 1) / (32 * MR_SUB);
+        if (w < nb)
+            p = cand;
+        else
+            w -= nb;
+    }
+    if (p < 0)
+        return;
+#else
+    for (p = 0; p < world; ++p)
     {
         np = off[p + 1] - off[p];
-        const u64 nb = (np + 31) >> 5;
+        const u64 nb = (np + 32 * MR_SUB - 1) / (32 * MR_SUB);
         if (w < nb)
             break;
         w -= nb;
     }
     if (p >= world)
         return;
+#endif
     const u64* kp = rec + (size_t)p * 2ull * cap;
-    const u64 i0 = w * 32, i = i0 + lane;
-    const bool valid = i < np;
-    const u64 K = valid ? __ldcg(kp + i) : ~0ull;
-    const u64 last = np - 1 - i0 < 31 ? np - 1 - i0 : 31;
-    const u64 K0 = __shfl_sync(0xffffffffu, K, 0), KL = __shfl_sync(0xffffffffu, K, (int)last);
+    const u64 i0 = w * 32 * MR_SUB;
+    const u64 iend = i0 + 32 * MR_SUB < np ? i0 + 32 * MR_SUB : np;
     const int q = lane & 15;
     u64 bracket = 0;
     if (q < world && q != p)
     {
         const u64* kq = rec + (size_t)q * 2ull * cap;
-        bracket = peer_lower_bound(kq, 0, off[q + 1] - off[q], lane < 16 ? K0 : KL);
+        bracket = peer_lower_bound(kq, 0, off[q + 1] - off[q], __ldcg(kp + (lane < 16 ? i0 : iend - 1)));
     }
-    u64 below = 0;
+    u64 K[MR_SUB];
+    u32 below[MR_SUB];
+#pragma unroll
+    for (int s = 0; s < MR_SUB; ++s)
+    {
+        const u64 i = i0 + (u64)s * 32 + lane;
+        K[s] = i < iend ? __ldcg(kp + i) : ~0ull;
+        below[s] = 0;
+    }
+    u64* st = stage[warp];
     for (int r = 0; r < world; ++r)
     {
-        const u64 lo = __shfl_sync(0xffffffffu, bracket, r), hi = __shfl_sync(0xffffffffu, bracket, 16 + r);
-        if (r != p && valid)
-            below += peer_lower_bound(rec + (size_t)r * 2ull * cap, lo, hi, K);
+        const u64 a = __shfl_sync(0xffffffffu, bracket, r), b = __shfl_sync(0xffffffffu, bracket, 16 + r);
+        if (r == p)
+            continue;
+        const u64* kr = rec + (size_t)r * 2ull * cap;
+        if (b - a > MR_STAGE_MAX)
+        { // a gap in this run's coverage facing a dense part of run r: few warps, searched per lane in global memory
+            // (the lane's MR_SUB searches advance together: a warp with long brackets in every run is the kernel's tail)
+            u32 lo[MR_SUB], len[MR_SUB];
+#pragma unroll
+            for (int s = 0; s < MR_SUB; ++s)
+            {
+                lo[s] = (u32)a;
+                len[s] = (u32)(b - a);
+            }
+            for (u32 m = (u32)(b - a); m > 0; m >>= 1)
+            {
+                u64 probe[MR_SUB];
+#pragma unroll
+                for (int s = 0; s < MR_SUB; ++s)
+                    probe[s] = len[s] ? __ldcg(kr + lo[s] + (len[s] >> 1)) : 0ull;
+#pragma unroll
+                for (int s = 0; s < MR_SUB; ++s)
+                {
+                    const u32 half = len[s] >> 1;
+                    const bool right = len[s] && probe[s] < K[s];
+                    lo[s] = right ? lo[s] + half + 1 : lo[s];
+                    len[s] = right ? len[s] - half - 1 : half;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < MR_SUB; ++s)
+                below[s] += lo[s];
+            continue;
+        }
+#pragma unroll
+        for (int s = 0; s < MR_SUB; ++s)
+            below[s] += (u32)a;
+        for (u64 c0 = a; c0 < b; c0 += MR_CH)
+        {
+            const u32 n = b - c0 < MR_CH ? (u32)(b - c0) : MR_CH;
+            for (u32 t = lane; t < n; t += 32)
+                st[t] = __ldcg(kr + c0 + t);
+            __syncwarp();
+            u32 lo[MR_SUB], len[MR_SUB];
+#pragma unroll
+            for (int s = 0; s < MR_SUB; ++s)
+            {
+                lo[s] = 0;
+                len[s] = n;
+            }
+            for (u32 m = n; m > 0; m >>= 1) // lower_bound of every key among the staged ones, branch-free
+            {
+#pragma unroll
+                for (int s = 0; s < MR_SUB; ++s)
+                {
+                    const u32 half = len[s] >> 1;
+                    const bool right = len[s] && st[lo[s] + half] < K[s];
+                    lo[s] = right ? lo[s] + half + 1 : lo[s];
+                    len[s] = right ? len[s] - half - 1 : half;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < MR_SUB; ++s)
+                below[s] += lo[s];
+            __syncwarp();
+        }
     }
-    if (valid)
+#pragma unroll
+    for (int s = 0; s < MR_SUB; ++s)
     {
-        const u64 gid = i + below;
-        keys_out[gid] = K;
-        corners_out[gid] = __ldcg(kp + cap + i);
+        const u64 i = i0 + (u64)s * 32 + lane;
+        if (i < iend)
+        {
+            const u64 gid = i + below[s];
+            keys_out[gid] = K[s];
+            corners_out[gid] = __ldcg(kp + cap + i);
+        }
     }
 }
 
@@ -397,7 +512,7 @@ extern "C"
         const int world = c->peer_world;
         const int parity = (int)(c->peer_seq & 1);
         u64* base = (u64*)c->peer_rx.p;
-        u64* off = c->scratch.as<u64>() + 4; // world + 1 offsets, then res[2]
+        u64* off = c->scratch.as<u64>() + 4; // world + 1 offsets, then res[2 + world] (total, status, runs by length)
         u64* res = off + VC_MAX_PEERS + 1;
         VC_LAUNCH(c, "peer_wait", k_peer_wait, 1, 32, 0, base + peer_hdr_off(parity, 0), world, c->peer_seq,
                   (u64)c->peer_cap, (u64)c->peer_timeout_ms * 1000000ull, off, res);
@@ -421,9 +536,9 @@ extern "C"
             *n_all = n;
         if (n > 0)
         { // merge the sorted runs by ranking: every record straight to its id
-            const size_t warps = (size_t)(n + 31) / 32 + (size_t)world;
+            const size_t warps = (size_t)(n + 32 * MR_SUB - 1) / (32 * MR_SUB) + (size_t)world;
             VC_LAUNCH(c, "merge_rank", k_merge_rank, vc_blocks(warps * 32, 256), 256, 0, base + peer_rec_off(world, c->peer_cap, parity, 0),
-                      world, (u64)c->peer_cap, off, keys, corners);
+                      world, (u64)c->peer_cap, off, res + 2, keys, corners);
         }
         return st_finalize_sites(c, keys, corners, n, VC_SITES_PRESORTED);
     }

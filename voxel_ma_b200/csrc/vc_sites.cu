@@ -961,32 +961,57 @@ __global__ void k_line_fill(const u64* __restrict__ site_corner, int64_t n, int 
 }
 
 // columns with up to LS_SHORT entries: one thread orders them with a compare-exchange network on the (cz, id)
-// words; longer ones are queued for k_line_sort_long.  dups (nullable) counts equal cz inside a column (external
-// sets with repeated points).
+// words; longer ones are queued by size class for k_line_sort_queued.  dups (nullable) counts equal cz inside a
+// column (external sets with repeated points).
+// queue[0..3] = number of queued columns of class 0 (5..8 entries), 1 (9..16), 2 (17..32), 3 (more); LsQueues = where
+// each class's queue starts inside `queue` (from the bound  #columns with > m entries <= n / (m + 1)).
 #define LS_SHORT 4
+#define LS_QHDR 4
+struct LsQueues
+{
+    u32 start[4];
+};
 __device__ __forceinline__ void ls_cx(u64& a, u64& b)
 {
     const u64 lo = a < b ? a : b, hi = a < b ? b : a;
     a = lo;
     b = hi;
 }
-__global__ void k_line_sort_short(const int* __restrict__ line_ptr, int nlines, const u64* __restrict__ tmp, u64* __restrict__ ent,
-                                  u32* __restrict__ long_lines, u32* __restrict__ nlong, u64* __restrict__ dups)
+__global__ void __launch_bounds__(256)
+    k_line_sort_short(const int* __restrict__ line_ptr, int nlines, const u64* __restrict__ tmp, u64* __restrict__ ent,
+                      u32* __restrict__ queue, LsQueues qs, u64* __restrict__ dups)
 {
+    // queue slots are handed out per block (shared-memory counters, then one global atomic per class and block):
+    // one global atomic per long column would serialise 2e5 of them on one address
+    __shared__ u32 s_cnt[4], s_base[4];
+    if (threadIdx.x < 4)
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlines)
+    int b = 0, cnt = 0;
+    if (l < nlines)
+    {
+        b = line_ptr[l];
+        cnt = line_ptr[l + 1] - b;
+    }
+    const int cls = cnt <= LS_SHORT ? -1 : cnt <= 8 ? 0 : cnt <= 16 ? 1 : cnt <= 32 ? 2 : 3;
+    u32 slot = 0;
+    if (cls >= 0)
+        slot = atomicAdd(&s_cnt[cls], 1u);
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x])
+        s_base[threadIdx.x] = atomicAdd(&queue[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (cls >= 0)
+    {
+        queue[qs.start[cls] + s_base[cls] + slot] = (u32)l;
         return;
-    const int b = line_ptr[l], cnt = line_ptr[l + 1] - b;
+    }
     if (cnt == 0)
         return;
     if (cnt == 1)
     {
         ent[b] = tmp[b];
-        return;
-    }
-    if (cnt > LS_SHORT)
-    {
-        long_lines[atomicAdd(nlong, 1u)] = (u32)l;
         return;
     }
     u64 e0 = tmp[b], e1 = tmp[b + 1], e2 = cnt > 2 ? tmp[b + 2] : VC_INF, e3 = cnt > 3 ? tmp[b + 3] : VC_INF;
@@ -1009,21 +1034,70 @@ __global__ void k_line_sort_short(const int* __restrict__ line_ptr, int nlines, 
     }
 }
 
+// Columns of 5..32 entries: W lanes per column (32 / W columns per warp), lane = entry; the place of an entry is the
+// number of smaller (cz, id) words in its group, counted over W shuffles (the words are distinct: ids are).  An entry
+// that has a smaller word with the same cz is a repeated point.
+template <int W>
+__device__ __forceinline__ void ls_rank_group(const int* __restrict__ line_ptr, const u64* __restrict__ tmp, u64* __restrict__ ent,
+                                              const u32* __restrict__ q, u32 nq, u32 item, int lane, u64* __restrict__ dups)
+{
+    const u32 j = item * (32 / W) + (u32)(lane / W);
+    const int sub = lane & (W - 1);
+    int b = 0, cnt = 0;
+    if (j < nq)
+    {
+        const int l = (int)q[j];
+        b = line_ptr[l];
+        cnt = line_ptr[l + 1] - b;
+    }
+    const bool mine = sub < cnt;
+    const u64 e = mine ? tmp[b + sub] : VC_INF;
+    u32 rank = 0, dup = 0;
+#pragma unroll
+    for (int s = 0; s < W; ++s)
+    {
+        const u64 o = __shfl_sync(0xffffffffu, e, s, W);
+        rank += o < e;
+        dup |= (o < e) & ((u32)(o >> 32) == (u32)(e >> 32));
+    }
+    if (mine)
+        ent[b + rank] = e;
+    const u32 nd = __popc(__ballot_sync(0xffffffffu, mine && dup));
+    if (nd && dups && lane == 0)
+        atomicAdd(dups, (u64)nd);
+}
+
 // Longer columns: one warp per column.  The cz of a column's sites are distinct corner indices in [0, nz], so the
 // column is ordered by presence: a bitmap of nz+1 bits in shared memory, rank = number of set bits below cz.
 // A bit found already set is a repeated point (only possible for external sets): it is counted in dups, which
 // makes the caller fall back to the general search -- the lists are then not used.
 #define LS_WORDS 65 // 2049 bits + padding: sides up to 2048
 __global__ void __launch_bounds__(256)
-    k_line_sort_long(const int* __restrict__ line_ptr, const u64* __restrict__ tmp, u64* __restrict__ ent,
-                     const u32* __restrict__ long_lines, const u32* __restrict__ nlong, u64* __restrict__ dups)
+    k_line_sort_queued(const int* __restrict__ line_ptr, const u64* __restrict__ tmp, u64* __restrict__ ent,
+                       const u32* __restrict__ queue, LsQueues qs, u64* __restrict__ dups)
 {
     __shared__ u32 bitsm[8][LS_WORDS + 1], pre[8][LS_WORDS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 nl = *nlong;
-    for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nl; j += (gridDim.x * blockDim.x) >> 5)
+    const u32 n0 = queue[0], n1 = queue[1], n2 = queue[2], n3 = queue[3];
+    const u32 i0 = (n0 + 3) >> 2, i1 = i0 + ((n1 + 1) >> 1), i2 = i1 + n2, i3 = i2 + n3; // warp-sized work items
+    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < i3; it += (gridDim.x * blockDim.x) >> 5)
     {
-        const int l = (int)long_lines[j];
+        if (it < i0)
+        {
+            ls_rank_group<8>(line_ptr, tmp, ent, queue + qs.start[0], n0, it, lane, dups);
+            continue;
+        }
+        if (it < i1)
+        {
+            ls_rank_group<16>(line_ptr, tmp, ent, queue + qs.start[1], n1, it - i0, lane, dups);
+            continue;
+        }
+        if (it < i2)
+        {
+            ls_rank_group<32>(line_ptr, tmp, ent, queue + qs.start[2], n2, it - i1, lane, dups);
+            continue;
+        }
+        const int l = (int)queue[qs.start[3] + (it - i2)];
         const int b = line_ptr[l], cnt = line_ptr[l + 1] - b;
         for (int w = lane; w <= LS_WORDS; w += 32)
             bitsm[warp][w] = 0;
@@ -1180,19 +1254,23 @@ int st_finalize_sites(vc_ctx* c, const u64* keys_dev, const u64* corners_dev, in
         u32* ptr = c->line_ptr.as<u32>();
         VC_CUDA(c, c->line_cur.ensure((size_t)(nlines + 2) * 4));
         u32* cursor = c->line_cur.as<u32>();
-        VC_CUDA(c, c->shist.ensure(((size_t)nlines + 4) * 4));
-        u32* long_lines = c->shist.as<u32>(); // [0] = count, then the queued columns
+        // queues of the columns with more than LS_SHORT entries, by size class: at most n / (m + 1) columns hold more
+        // than m entries
+        const u32 qcap[4] = {(u32)(n / 5 + 1), (u32)(n / 9 + 1), (u32)(n / 17 + 1), (u32)(n / 33 + 1)};
+        const LsQueues qs = {{LS_QHDR, LS_QHDR + qcap[0], LS_QHDR + qcap[0] + qcap[1], LS_QHDR + qcap[0] + qcap[1] + qcap[2]}};
+        VC_CUDA(c, c->shist.ensure(((size_t)qs.start[3] + qcap[3]) * 4));
+        u32* queue = c->shist.as<u32>();
         VC_CUDA(c, cudaMemsetAsync(ptr, 0, (size_t)(nlines + 2) * 4, c->stream));
-        VC_CUDA(c, cudaMemsetAsync(long_lines, 0, 4, c->stream));
+        VC_CUDA(c, cudaMemsetAsync(queue, 0, LS_QHDR * 4, c->stream));
         VC_CUDA(c, cudaMemsetAsync(counter, 0, 16, c->stream));
         VC_LAUNCH(c, "line_count", k_line_count, blocks, 256, 0, c->site_corner.as<u64>(), n, CY, ptr);
         VC_TRY(vc_exclusive_scan_u32(c, ptr, len));
         VC_CUDA(c, cudaMemcpyAsync(cursor, ptr, (size_t)(nlines + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
         VC_LAUNCH(c, "line_fill", k_line_fill, blocks, 256, 0, c->site_corner.as<u64>(), n, CY, cursor, k2);
         VC_LAUNCH(c, "line_sort", k_line_sort_short, vc_blocks((size_t)nlines, 256), 256, 0, c->line_ptr.as<int>(), nlines, k2,
-                  c->line_ent.as<u64>(), long_lines + 1, long_lines, external ? counter : (u64*)nullptr);
-        VC_LAUNCH(c, "line_sort", k_line_sort_long, c->sm_count * 2, 256, 0, c->line_ptr.as<int>(), k2, c->line_ent.as<u64>(),
-                  long_lines + 1, long_lines, external ? counter : (u64*)nullptr);
+                  c->line_ent.as<u64>(), queue, qs, external ? counter : (u64*)nullptr);
+        VC_LAUNCH(c, "line_sort", k_line_sort_queued, c->sm_count * 4, 256, 0, c->line_ptr.as<int>(), k2, c->line_ent.as<u64>(),
+                  queue, qs, external ? counter : (u64*)nullptr);
     }
     {
         const int CX = c->nx + 1, CY = c->ny + 1, nw = (CX + 31) >> 5;
