@@ -361,6 +361,7 @@ def points_path(ctx, grid, args, nq=4_000_000):
     worst case for an expanding-shell search: uniformly random points of the whole box (most of them far from any site)."""
     nx, ny, nz = grid
     rng = np.random.default_rng(11)
+    ctx.run_dense()  # the end-to-end legs before this one leave no dense planes behind
     vert = ctx.compact_records()[0].astype(np.int64)
     pick = vert[rng.integers(0, len(vert), nq)]
     q_in = np.stack([pick % nx, (pick // nx) % ny, pick // (nx * ny)], -1).astype(np.float64) + rng.uniform(-0.5, 0.5, (nq, 3))
@@ -730,7 +731,7 @@ def measure(args, fam, grid, scaling, dist, rank, world, local, sub=False):
                                              "each step) + sites + closest + measures; wall clock per step"}
             except Exception as ex:
                 line["mesh_path"] = {"error": repr(ex)}
-    if rank == 0 and world == 1 and not args.no_points:
+    if rank == 0 and world == 1 and not args.no_points and not sub:
         # the arbitrary-point query path (vc_closest_points: the drop-in for ANNkd_tree::annkSearch(k=1, eps=0) behind
         # voxelapps / estimateRadiiField): uniformly random float64 queries in the grid's box over this workload's sites,
         # host arrays in and out; next to it the reference's kd-tree on all host cores over a sample of the same queries

@@ -15,6 +15,9 @@ VARIANTS = {
     "mr8": ["-DMR_SUB=8"],
     "mr16": ["-DMR_SUB=16"],
     "mr1": ["-DMR_SUB=1"],
+    "t64": ["-DXY_THREADS=64", "-DXY_MINB=16"],
+    "t32": ["-DXY_THREADS=32", "-DXY_MINB=32"],
+    "t256": ["-DXY_THREADS=256", "-DXY_MINB=4"],
     "mr_noorder": ["-DMR_ORDER=0"],
     "mr8o": ["-DMR_SUB=8"],
     "mr4o_s1024": ["-DMR_STAGE_MAX=1024"],

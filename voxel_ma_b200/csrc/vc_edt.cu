@@ -161,7 +161,9 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+#ifndef XY_THREADS
 #define XY_THREADS 128
+#endif
 
 // ---- envelope stack storage on the device ----------------------------------------------------------
 // Entries are 16 bytes (g, id, p, start): one LDS.128 / STS.128, nothing to pack.  The top of the stack lives
@@ -505,11 +507,14 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         return st_measures(c, want_radius);
     }
     const int nplanes_all = c->zc - c->z0;
-    const int nw = c->profiling ? 0 : c->nworkers;
+    int nw = c->profiling ? 0 : c->nworkers;
     // chunk height: a multiple of 32 planes (pass X puts 32 planes in a warp), >= 64 planes and >= 32k lines per
     // launch so that a chunk's kernels are efficient on their own, and no more chunks than about one per worker stream;
     // VC_ZCHUNK overrides.  Fewer than three chunks do not pay (measured: two are slower than one -- a 129-plane slab of
-    // a 1024^2 grid runs 4.11 ms as one chunk, 4.30 as four, 4.40 as two), so a thin slab is one chunk.
+    // a 1024^2 grid runs 4.11 ms as one chunk, 4.30 as four, 4.40 as two), so a thin slab is one chunk.  (Chunks of a
+    // thin slab started one stage apart, so that different stages overlap, are worse still -- 3.8 ms for two, 5.9 for four
+    // against 3.05: a pass over a quarter of the planes takes about as long as over all of them, its duration is the
+    // sequential scan of the longest lines, not the number of lines.)
     int zchunk = c->zchunk;
     if (zchunk <= 0)
     {
@@ -525,6 +530,8 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         zchunk = nplanes_all;
     // the last chunk takes the remainder (a slab's halo plane, for one) instead of becoming a launch of its own
     const int nchunks = nplanes_all / zchunk > 1 ? nplanes_all / zchunk : 1;
+    if (nchunks == 1)
+        nw = 0; // nothing to overlap: the fork / join events around a single chunk cost 0.06 ms
     const int region_planes = nplanes_all - (nchunks - 1) * zchunk;
     VC_TRY(edt_alloc(c, nchunks, region_planes));
     if (!c->have_inside)
