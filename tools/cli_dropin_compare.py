@@ -26,12 +26,13 @@ def run(exe, vol):
         synth.write_mrc(os.path.join(d, "vol.mrc"), vol)
         subprocess.check_call(["cp", os.path.join(os.path.dirname(exe), "cycle8.txt"), d])
         t0 = time.perf_counter()
-        r = subprocess.run([exe, *ARGS], cwd=d, capture_output=True, text=True)
+        r = subprocess.run([exe, *ARGS], cwd=d, capture_output=True, text=True, env=dict(os.environ, VC_DROPIN_TRACE="1"))
         dt = time.perf_counter() - t0
         files = {f: hashlib.sha256(open(os.path.join(d, f), "rb").read()).hexdigest()
                  for f in sorted(os.listdir(d)) if f.startswith("out")}
         stages = [l.strip() for l in r.stdout.splitlines() if l.startswith("time")]
-    return r.returncode, dt, files, stages
+        trace = [l.strip()[len("[vc dropin] "):] for l in r.stderr.splitlines() if l.startswith("[vc dropin]")]
+    return r.returncode, dt, files, stages, trace
 
 
 def main():
@@ -39,12 +40,12 @@ def main():
     for spec in sys.argv[1:] or ["sphere:64"]:
         kind, n = spec.split(":")
         vol = getattr(synth, kind)(int(n))
-        rc_r, t_r, f_r, s_r = run(REF, vol)
-        rc_g, t_g, f_g, s_g = run(GPU, vol)
+        rc_r, t_r, f_r, s_r, _ = run(REF, vol)
+        rc_g, t_g, f_g, s_g, tr_g = run(GPU, vol)
         same = rc_r == 0 and rc_g == 0 and f_r == f_g and len(f_r) > 0
         ok &= same
         print(json.dumps({"volume": spec, "identical_outputs": same, "files": sorted(f_r), "ref_wall_s": round(t_r, 3),
-                          "gpu_cli_wall_s": round(t_g, 3), "rc": [rc_r, rc_g], "ref_stages": s_r, "gpu_stages": s_g}))
+                          "gpu_cli_wall_s": round(t_g, 3), "rc": [rc_r, rc_g], "ref_stages": s_r, "gpu_stages": s_g, "gpu_trace": tr_g}))
     sys.exit(0 if ok else 1)
 
 

@@ -40,7 +40,9 @@ void CellComplexThinning::prune(float _f_t, float _l_t, bool _remove_small_compo
     m_removed[FACE].assign(nF, false);
     m_removed[VERTEX].assign(nV, false);
     m_to_remove_face.assign(nF, false);
+    vcgpu::TraceScope tr_all("CellComplexThinning::prune (GPU seeding + the reference's loop)");
     std::vector<int32_t> ends, face_edges, f;
+    vcgpu::TraceScope* tr = new vcgpu::TraceScope("prune: incidence lists to flat arrays");
     ends.reserve(2 * nE);
     for (int64_t e = 0; e < nE; ++e)
     {
@@ -55,12 +57,16 @@ void CellComplexThinning::prune(float _f_t, float _l_t, bool _remove_small_compo
     }
     m_ref_vert_per_prune.assign(nV, 0);
     m_ref_edge_per_prune.assign(nE, 0);
+    delete tr;
+    tr = new vcgpu::TraceScope("prune: 2 x vc_ref_counts");
     if (!s.check(vc_ref_counts(s.ctx(), ends.data(), (int64_t)ends.size(), nV, m_ref_vert_per_prune.data()), "vc_ref_counts") ||
         !s.check(vc_ref_counts(s.ctx(), face_edges.data(), (int64_t)face_edges.size(), nE, m_ref_edge_per_prune.data()), "vc_ref_counts"))
         die("prune");
 
+    delete tr;
     // 02. seed the queue: first incident face of every edge / first incident edge of every vertex
     std::cout << "init.ing q ..." << std::endl;
+    tr = new vcgpu::TraceScope("prune: first-neighbour arrays + vc_simple_pairs + queue fill");
     std::vector<int32_t> edge_face0(nE, 0), vert_edge0(nV, 0);
     for (int64_t e = 0; e < nE; ++e)
         if (m_ref_edge_per_prune[e] > 0)
@@ -79,6 +85,7 @@ void CellComplexThinning::prune(float _f_t, float _l_t, bool _remove_small_compo
     for (int64_t i = 0; i < np; ++i)
         q.push(simple_pair((simple_pair::spairtype)pairs[3 * i], (unsigned)pairs[3 * i + 1], (unsigned)pairs[3 * i + 2]));
     std::cout << "after init, q size: " << q.size() << "" << std::endl;
+    delete tr;
 
     // 03. iterative retraction: the reference's own loop
     std::set<unsigned> vts_to_debug;

@@ -33,6 +33,7 @@ struct WarmUp
     WarmUp()
     {
         t = std::thread([] {
+            vcgpu::TraceScope tr("vc_warmup (helper thread, from process start)");
             const char* dev = std::getenv("VC_DEVICE");
             vc_warmup(dev ? std::atoi(dev) : 0);
         });

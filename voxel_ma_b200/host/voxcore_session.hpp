@@ -37,8 +37,12 @@ struct TraceScope
     ~TraceScope()
     {
         if (on)
-            std::cerr << "[vc dropin] " << what << ": "
-                      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << " ms" << std::endl;
+        {
+            static const std::chrono::steady_clock::time_point first = t0; // the first scope's start: close to process start
+            const auto now = std::chrono::steady_clock::now();
+            std::cerr << "[vc dropin] " << what << ": " << std::chrono::duration<double, std::milli>(now - t0).count() << " ms (at "
+                      << std::chrono::duration<double, std::milli>(now - first).count() << " ms)" << std::endl;
+        }
     }
 };
 
@@ -172,6 +176,7 @@ public:
 private:
     Session()
     {
+        TraceScope ts("vc_ctx_create");
         const char* dev = std::getenv("VC_DEVICE");
         vc_ctx* c = nullptr;
         int st = vc_ctx_create(dev ? std::atoi(dev) : 0, &c);
@@ -186,6 +191,7 @@ private:
     }
     ~Session()
     {
+        TraceScope ts("vc_ctx_destroy");
         if (m_ctx)
             vc_ctx_destroy(m_ctx);
     }
