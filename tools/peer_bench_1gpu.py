@@ -8,6 +8,7 @@ runs its closest-site transform and measures.  The contexts share the GPU, so on
 mean anything (profiled: events around every launch) -- what the site pipeline of one rank costs per step (merge_rank,
 line_sort, tables, pass Z) without paying for eight GPUs.  The slab bounds are bench.py's (slabs.aligned_bounds)."""
 import json
+import os
 import sys
 
 import numpy as np
@@ -23,15 +24,16 @@ fam, n = wl.split(":")
 n = int(n)
 nx = ny = nz = n
 bounds = slabs.aligned_bounds(np.ones(nz), world, 32)
+ndev = int(os.environ.get("VC_PEER_DEVICES", "1"))  # > 1: context k on device k % ndev (stores cross NVLink: ncu nvltx / nvlrx)
 parts = []
 for k in range(world):
     z0, z1 = bounds[k]
     lo, hi = max(z0 - 1, 0), min(z1 + 1, nz)
-    c = api.Context(0)
+    c = api.Context(k % ndev)
     c.set_grid(nx, ny, nz, z0, z1)
     c.upload_volume(synth.make(fam, n, z0=lo, z1=hi), zlo=lo)
     parts.append(c)
-cap = 1 << 20
+cap = (6 << 20) // world + (1 << 18)
 for k, c in enumerate(parts):
     c.peer_create(world, k, cap)
 bases = [c.peer_buffer() for c in parts]
