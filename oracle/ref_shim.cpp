@@ -438,6 +438,21 @@ extern "C"
         memcpy(xyz, p->tet_vpts.data(), p->tet_vpts.size() * sizeof(float));
         memcpy(tag, p->tet_vtag.data(), p->tet_vtag.size());
     }
+    // extractInsideWithMeasure outputs (after preprocess): the inside complex handed to cellcomplex / CellComplexThinning
+    // (src/highlevelalgo.cpp:738-741, 819-822); counts = ref_pipeline_count 5 / 6 / 7
+    void ref_pipeline_inside(void* h, float* vts, int32_t* edges, int32_t* tris)
+    {
+        auto* p = (Pipeline*)h;
+        for (size_t i = 0; i < p->out_vts.size(); ++i)
+            for (int k = 0; k < 3; ++k)
+                vts[3 * i + k] = p->out_vts[i][k];
+        for (size_t i = 0; i < p->out_edges.size(); ++i)
+            for (int k = 0; k < 2; ++k)
+                edges[2 * i + k] = p->out_edges[i][k];
+        for (size_t i = 0; i < p->out_tris.size(); ++i)
+            for (int k = 0; k < 3; ++k)
+                tris[3 * i + k] = (int32_t)p->out_tris[i][k];
+    }
     // extractInsideWithMeasure outputs (after preprocess): V/E/F measures
     void ref_pipeline_measures(void* h, float* v_m, float* e_m, float* f_m, int32_t* from_fi)
     {

@@ -41,3 +41,18 @@ def test_simple_pairs_rejects_bad_neighbour(ctx):
     c["edge_face0"][5] = 10_000
     with pytest.raises(api.VoxcoreError, match="first-neighbour"):
         ctx.simple_pairs(**c)
+
+
+def test_seeding_matches_the_reference_queue(ctx):
+    """the queue the unmodified compiled CellComplexThinning::prune seeded (tests/golden/thin_seed_sphere24.npz, made by
+    tests/golden/make_thin_golden.py through oracle/ref_thinspy.cpp): same pairs in the same order from vc_simple_pairs,
+    the same reference counts from vc_ref_counts on the complex's own incidence lists"""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "thin_seed_sphere24.npz"))
+    for tag in ("lo", "mid", "hi"):
+        c = {k: d[f"{tag}_{k}"] for k in ("edge_ref", "edge_face0", "face_measure", "vert_ref", "vert_edge0", "edge_measure",
+                                          "face_to_remove")}
+        got = ctx.simple_pairs(f_t=float(d[f"{tag}_f_t"]), l_t=float(d[f"{tag}_l_t"]), **c)
+        assert np.array_equal(got, d[f"{tag}_pairs"]), tag
+        assert np.array_equal(ctx.ref_counts(d[f"{tag}_edge_ends"], len(c["vert_ref"])), c["vert_ref"])
+        assert np.array_equal(ctx.ref_counts(d[f"{tag}_face_edges"], len(c["edge_ref"])), c["edge_ref"])

@@ -41,3 +41,19 @@ def test_reference_cli_queue_size_is_recorded():
     """the pin used by the GPU CLI test: `after init, q size: 5472` on sphere64 (unmodified reference)"""
     txt = open(os.path.join(HERE, "golden", "cli_sphere64.txt")).read()
     assert re.search(r"after init, q size: 5472", txt)
+
+
+def test_oracle_seeding_matches_the_reference_queue():
+    """tests/golden/thin_seed_sphere24.npz holds the queue the UNMODIFIED compiled CellComplexThinning::prune seeded on the
+    reference's own inside complex of sphere24 (captured through the interposed prune_while_iteration,
+    oracle/ref_thinspy.cpp), in push order, for three thresholds -- and the state it read.  The oracle's K6 must
+    reproduce it exactly, and its reference counts must be the histograms of the complex's incidence lists."""
+    d = np.load(os.path.join(HERE, "golden", "thin_seed_sphere24.npz"))
+    for tag in ("lo", "mid", "hi"):
+        c = {k: d[f"{tag}_{k}"] for k in ("edge_ref", "edge_face0", "face_measure", "vert_ref", "vert_edge0", "edge_measure",
+                                          "face_to_remove")}
+        got = ob.simple_pairs(f_t=float(d[f"{tag}_f_t"]), l_t=float(d[f"{tag}_l_t"]), **c)
+        assert np.array_equal(got, d[f"{tag}_pairs"]), tag
+        assert np.array_equal(ob.ref_counts(d[f"{tag}_edge_ends"], len(c["vert_ref"])), c["vert_ref"])
+        assert np.array_equal(ob.ref_counts(d[f"{tag}_face_edges"], len(c["edge_ref"])), c["edge_ref"])
+    assert len(d["mid_pairs"]) > 100 and len(d["lo_pairs"]) < len(d["mid_pairs"])
