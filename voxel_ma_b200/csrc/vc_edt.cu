@@ -572,7 +572,7 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
         const int ma = k == 0 ? c->z0 : zb - 1;
         const int mb = ze >= c->zc ? c->z1 : ze - 1;
         if (ma < mb && dense_measures)
-            status = measures_range(c, ma, mb, want_radius);
+            status = measures_range(c, ma, mb, want_radius, nchunks == 1);
         if (status == VC_OK && ma < mb && c->chunk_hook)
             status = c->chunk_hook(ma, mb); // e.g. compaction + device-to-host copy of this chunk's records
     }

@@ -222,7 +222,7 @@ int st_measures(vc_ctx* c, bool want_radius);
 int st_closest_measures_pipelined(vc_ctx* c, bool want_radius);
 // building blocks: planes [zb,ze) of the slab on stream c->cur
 int edt_range(vc_ctx* c, int zb, int ze, int region, int region_planes);
-int measures_range(vc_ctx* c, int za, int zb, bool want_radius);
+int measures_range(vc_ctx* c, int za, int zb, bool want_radius, bool alone);
 int measures_alloc(vc_ctx* c, bool want_radius);
 int st_classify_points(vc_ctx* c, const float* xyz, int64_t n, const double* M, uint8_t* out);
 int st_face_lambda(vc_ctx* c, const int32_t* pairs, int64_t nf, float* out);

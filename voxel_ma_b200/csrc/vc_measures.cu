@@ -386,16 +386,24 @@ int measures_alloc(vc_ctx* c, bool want_radius)
     return VC_OK;
 }
 
-// measures of the anchor planes [za, zb) of the slab, on stream c->cur (buffers from measures_alloc)
-int measures_range(vc_ctx* c, int za, int zb, bool want_radius)
+// measures of the anchor planes [za, zb) of the slab, on stream c->cur (buffers from measures_alloc); `alone`: nothing
+// else runs beside this launch (a slab transformed as one chunk, vc_cell_measures_grid)
+int measures_range(vc_ctx* c, int za, int zb, bool want_radius, bool alone)
 {
-    // z chunks per block: long enough to amortise the one extra plane a block loads, short enough that
-    // the grid is several waves of the SMs
+    // z chunks per block: long enough to amortise the one extra plane a block loads, short enough that the grid is
+    // many waves of the SMs.  A launch that has the device to itself pays its tail in full and wants ~ 110 blocks per
+    // SM (measured on a 127-plane slab of 1024^2: 1.25 ms at 32 planes per block = 4096 blocks, 1.14 at 16, 1.10 at
+    // 8 = 16384 blocks; twist512 whole: 0.95 / 0.89 / 0.86); the launches of a chunk pipeline overlap other kernels and
+    // are best at the long chunk (1024^3 in 128-plane chunks: 21.28 ms per step at 32, 21.46 at 8).
     const int nplanes = zb - za;
     const unsigned gx = (c->nx + CM_TW - 1) / CM_TW, gy = (c->ny + CM_TH - 1) / CM_TH;
+    const size_t want_blocks = (size_t)c->sm_count * (alone ? 110 : 16);
     int zchunk = 32;
-    while (zchunk > 4 && (size_t)gx * gy * ((nplanes + zchunk - 1) / zchunk) < (size_t)c->sm_count * 16)
+    while (zchunk > (alone ? 8 : 4) && (size_t)gx * gy * ((nplanes + zchunk - 1) / zchunk) < want_blocks)
         zchunk >>= 1;
+    static const int zchunk_env = getenv("VC_MEASURE_ZCHUNK") ? atoi(getenv("VC_MEASURE_ZCHUNK")) : 0; // A/B runs
+    if (zchunk_env > 0)
+        zchunk = zchunk_env;
     dim3 grid(gx, gy, (nplanes + zchunk - 1) / zchunk);
     if (grid.y > 65535u || grid.z > 65535u)
         return vc_fail(c, VC_ERR_UNSUPPORTED, "grid too large for the measures kernel");
@@ -420,7 +428,7 @@ int st_measures(vc_ctx* c, bool want_radius)
     if (c->zhi < c->zc)
         return vc_fail(c, VC_ERR_STATE, "inside flags do not cover the halo plane");
     VC_TRY(measures_alloc(c, want_radius));
-    VC_TRY(measures_range(c, c->z0, c->z1, want_radius));
+    VC_TRY(measures_range(c, c->z0, c->z1, want_radius, true));
     VC_CUDA(c, cudaGetLastError());
     c->have_measures = true;
     return VC_OK;
