@@ -515,13 +515,20 @@ int st_closest_measures_pipelined(vc_ctx* c, bool want_radius)
     // thin slab started one stage apart, so that different stages overlap, are worse still -- 3.8 ms for two, 5.9 for four
     // against 3.05: a pass over a quarter of the planes takes about as long as over all of them, its duration is the
     // sequential scan of the longest lines, not the number of lines.)
+    // When every chunk's records are copied to the host as it completes (chunk_hook: vc_run_dense_host_compact), the
+    // copies should start early and run throughout: short chunks on few streams, so that chunks complete one after
+    // another instead of all at the end (assembly1024: 1.33 GB of records; 111.8 ms per call with 8 chunks on 8 streams,
+    // 103.3 ms with 16 chunks on 4 -- the copy-back is then hidden behind the transform except for its last chunk).
+    const bool copy_back = c->chunk_hook != nullptr;
+    if (copy_back && nw > 4 && c->zchunk <= 0)
+        nw = 4;
     int zchunk = c->zchunk;
     if (zchunk <= 0)
     {
         const int side = c->nx < c->ny ? c->nx : c->ny;
         zchunk = (32768 + side - 1) / side;
         zchunk = ((zchunk < 64 ? 64 : zchunk) + 31) / 32 * 32;
-        const int per_worker = ((nplanes_all + (nw > 0 ? nw : 1) - 1) / (nw > 0 ? nw : 1) + 31) / 32 * 32;
+        const int per_worker = copy_back ? 0 : ((nplanes_all + (nw > 0 ? nw : 1) - 1) / (nw > 0 ? nw : 1) + 31) / 32 * 32;
         zchunk = zchunk < per_worker ? per_worker : zchunk;
         if (nplanes_all / zchunk < 3)
             zchunk = nplanes_all;
