@@ -15,6 +15,10 @@ VARIANTS = {
     "mr8": ["-DMR_SUB=8"],
     "mr16": ["-DMR_SUB=16"],
     "mr1": ["-DMR_SUB=1"],
+    "d8_pf16": ["-DED_DEPTH=8", "-DED_PFD=16"],
+    "minb6": ["-DXY_MINB=6"],
+    "minb4": ["-DXY_MINB=4"],
+    "ring16_minb4": ["-DXY_MINB=4", "-DSR_RX=16", "-DSR_RY=16"],
     "t64": ["-DXY_THREADS=64", "-DXY_MINB=16"],
     "t32": ["-DXY_THREADS=32", "-DXY_MINB=32"],
     "t256": ["-DXY_THREADS=256", "-DXY_MINB=4"],
