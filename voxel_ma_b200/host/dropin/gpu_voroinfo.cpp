@@ -47,9 +47,16 @@ static void all_face_lambdas(const std::vector<point>& sites, const std::vector<
     Session& s = Session::get();
     static_assert(sizeof(point) == 12 && sizeof(ivec2) == 8, "trimesh::Vec is a plain array");
     TraceScope tr("all_face_lambdas (set_sites + vc_face_lambda)");
-    if (!s.set_sites(sites.empty() ? nullptr : &sites[0][0], (int64_t)sites.size()))
-        die("vc_set_sites");
-    lam.assign(face_sites.size(), 0.0f);
+    {
+        TraceScope t1("  set_sites (fingerprint, upload when the set changed)");
+        if (!s.set_sites(sites.empty() ? nullptr : &sites[0][0], (int64_t)sites.size()))
+            die("vc_set_sites");
+    }
+    {
+        TraceScope t2("  result vector");
+        lam.assign(face_sites.size(), 0.0f);
+    }
+    TraceScope t3("  vc_face_lambda");
     if (!face_sites.empty() &&
         !s.check(vc_face_lambda(s.ctx(), &face_sites[0][0], (int64_t)face_sites.size(), lam.data()), "vc_face_lambda"))
         die("vc_face_lambda");
