@@ -15,6 +15,8 @@ VARIANTS = {
     "mr8": ["-DMR_SUB=8"],
     "mr16": ["-DMR_SUB=16"],
     "mr1": ["-DMR_SUB=1"],
+    "pz16": ["-DPZ_BLOCKS_PER_SM=16"],
+    "pz12": ["-DPZ_BLOCKS_PER_SM=12"],
     "d8_pf16": ["-DED_DEPTH=8", "-DED_PFD=16"],
     "minb6": ["-DXY_MINB=6"],
     "minb4": ["-DXY_MINB=4"],
